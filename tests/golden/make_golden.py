@@ -1,0 +1,213 @@
+"""Generate golden fixtures by running the UNMODIFIED reference here.
+
+    python tests/golden/make_golden.py seg
+    python tests/golden/make_golden.py depth
+
+Runs only in the build container (needs /root/reference).  It builds the
+reference's own classes from the reference's own config files
+(``segmentation/configs/...``, ``depth/configs/...``) through the import shim
+in ``refshim.py``, loads the seeded weights of ``oracle.ddp_oracle.make_weights``
+into them by state-dict key, calls ``DDP.ddim_sample`` / ``DDP.sample`` on
+seeded inputs and stores outputs (+ per-step head outputs) as ``.npz``.
+
+The fixtures hold seeds, shapes, checksums of the inputs and the reference's
+outputs; ``tests/test_oracle_golden.py`` regenerates inputs from the seeds and
+compares the oracle with the stored outputs.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+import refshim  # noqa: E402
+from oracle import ddp_oracle as O  # noqa: E402
+
+SEG_CASES = [
+    # name, config file, class override, num_classes, T, R, accumulation, h, w, wseed, xseed
+    dict(name="seg_city_T3", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
+         T=None, R=1, h=12, w=20, wseed=11, xseed=101),
+    dict(name="seg_ade_T3_acc", cfg="ade/ddp_swin_t_2x8_512x512_160k_ade20k.py",
+         T=None, R=1, h=16, w=16, wseed=12, xseed=102),
+    dict(name="seg_aligned_T10_R2", cfg="cityscapes/ddp_convnext_t_4x4_512x1024_5k_cityscapes_aligned.py",
+         T=None, R=2, h=8, w=16, wseed=13, xseed=103),
+    dict(name="seg_plumbing_T1_64x64", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
+         T=1, R=1, h=64, w=64, wseed=14, xseed=104),
+    dict(name="seg_city_T3_R3_ragged", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
+         T=None, R=3, h=7, w=13, wseed=15, xseed=105),
+]
+DEPTH_CASES = [
+    dict(name="depth_nyu_T3", cfg="ddp_nyu/ddp_swint_1k_w7_nyu_bs2x8_scale01.py",
+         T=None, R=1, h=12, w=16, wseed=21, xseed=201),
+    dict(name="depth_nyu_T20_R2", cfg="ddp_nyu/ddp_swint_1k_w7_nyu_bs2x8_scale01.py",
+         T=20, R=2, h=9, w=11, wseed=22, xseed=202),
+]
+
+
+def checksum(t):
+    t = t.double()
+    return np.array([float(t.sum()), float(t.abs().sum())])
+
+
+def load_weights(model, W):
+    sd = model.state_dict()
+    hot = [k for k in sd if not k.startswith(("backbone.", "neck.", "auxiliary_head."))]
+    missing = [k for k in hot if k not in W]
+    extra = [k for k in W if k not in sd]
+    assert not missing and not extra, (missing, extra)
+    for k in hot:
+        assert tuple(sd[k].shape) == tuple(W[k].shape), (k, sd[k].shape, W[k].shape)
+    model.load_state_dict(W, strict=False)
+
+
+def record_head(model, store):
+    orig = model._decode_head_forward_test
+
+    def wrapped(x, t, img_metas):
+        out = orig(x, t, img_metas)
+        store.append(out.detach().clone())
+        return out
+    model._decode_head_forward_test = wrapped
+
+
+def run_seg():
+    refshim.install("segmentation")
+    # the aligned configs do custom_imports='mmcls.models' (absent here; only provides the backbone)
+    for n in ("mmcls", "mmcls.models"):
+        sys.modules[n] = types.ModuleType(n)
+    import mmcv  # noqa: F401
+    from mmcv import Config
+    # mmcls.ConvNeXt (aligned configs) is not importable here; the backbone never runs in ddim_sample.
+    from mmseg.models import build_segmentor
+    from mmseg.models.builder import BACKBONES
+
+    @BACKBONES.register_module(name="NoBackbone")
+    class _NoBackbone(torch.nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+
+        def init_weights(self):
+            pass
+
+    for case in SEG_CASES:
+        cfg = Config.fromfile(f"{refshim.REF}/segmentation/configs/{case['cfg']}")
+        m = cfg.model
+        m.pretrained = None
+        if m.backbone.type.startswith("mmcls."):
+            m.backbone = dict(type="NoBackbone")       # scoped mmcls type is unresolvable here
+        if "init_cfg" in m.backbone:
+            m.backbone.init_cfg = None
+        m.auxiliary_head.norm_cfg = dict(type="BN")   # SyncBN -> BN, as tools/test.py:278 does
+        m.decode_head.norm_cfg = dict(type="BN")
+        if case["T"] is not None:
+            m.timesteps = case["T"]
+        m.randsteps = case["R"]
+        model = build_segmentor(m)
+        model.eval()
+        ocfg = O.OracleConfig(task="seg", num_classes=m.decode_head.num_classes, timesteps=m.timesteps,
+                              randsteps=case["R"], bit_scale=m.bit_scale,
+                              accumulation=bool(m.get("accumulation", False)))
+        W = O.make_weights(ocfg, seed=case["wseed"])
+        load_weights(model, W)
+        h, w, R = case["h"], case["w"], case["R"]
+        x = torch.randn(1, 256, h, w, generator=torch.Generator().manual_seed(case["xseed"]))
+        nseed = case["xseed"] + 1000
+        torch.manual_seed(nseed)
+        noise = torch.randn((R, 256, h, w))            # what ddp.py:220 will draw
+        steps = []
+        record_head(model, steps)
+        torch.manual_seed(nseed)
+        out = model.ddim_sample(x, None)
+        np.savez_compressed(
+            os.path.join(HERE, case["name"] + ".npz"),
+            task="seg", model_type=m.type, config=case["cfg"], num_classes=ocfg.num_classes,
+            timesteps=ocfg.timesteps, randsteps=R, bit_scale=ocfg.bit_scale,
+            accumulation=ocfg.accumulation, h=h, w=w, wseed=case["wseed"], xseed=case["xseed"],
+            nseed=nseed, x_checksum=checksum(x), noise_checksum=checksum(noise),
+            w_checksum=checksum(torch.cat([v.flatten() for _, v in sorted(W.items())])),
+            out=out.numpy(), step_logits=torch.stack(steps).numpy().astype(np.float32),
+            step_argmax=torch.stack(steps).argmax(2).numpy().astype(np.int16))
+        print(case["name"], m.type, tuple(out.shape), float(out.abs().mean()))
+
+
+def run_depth():
+    refshim.install("depth")
+    for n in ("timm", "timm.models", "timm.models.layers", "matplotlib", "matplotlib.pyplot",
+              "matplotlib.cm", "matplotlib.colors"):
+        class _Any(types.ModuleType):
+            def __getattr__(self, k):
+                if k.startswith("__"):
+                    raise AttributeError(k)
+                return _Any(self.__name__ + "." + k)
+
+            def __call__(self, *a, **k):
+                return None
+        sys.modules[n] = _Any(n)
+    import mmcv  # noqa: F401
+    # depth/depth/models/depther/__init__.py imports a module that is not in the tree
+    # (regulardepth); load the two files we need without running that __init__.
+    dp = types.ModuleType("depth.models.depther")
+    dp.__path__ = [f"{refshim.REF}/depth/depth/models/depther"]
+    sys.modules["depth.models.depther"] = dp
+    from depth.models import build_depther
+    import depth.models.depther.ddp  # noqa: F401
+    # The depth tree has no time-aware BaseTransformerLayer (it relies on a
+    # patched site-packages mmcv); the segmentation fork is the in-tree statement of that layer.
+    import importlib.util
+    from mmcv.utils.registry import Registry
+    orig = Registry._register_module
+
+    def forced(self, module_class, module_name=None, force=False):
+        return orig(self, module_class, module_name, True)
+    Registry._register_module = forced
+    spec = importlib.util.spec_from_file_location(
+        "seg_transformer_fork", f"{refshim.REF}/segmentation/mmseg/models/utils/transformer.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Registry._register_module = orig
+    from mmcv import Config
+
+    for case in DEPTH_CASES:
+        cfg = Config.fromfile(f"{refshim.REF}/depth/configs/{case['cfg']}")
+        m = cfg.model
+        m.backbone.init_cfg = None
+        if case["T"] is not None:
+            m.timesteps = case["T"]
+        m.randsteps = case["R"]
+        model = build_depther(m)
+        model.eval()
+        ocfg = O.OracleConfig(task="depth", timesteps=m.timesteps, randsteps=case["R"],
+                              bit_scale=m.bit_scale, min_depth=m.min_depth, max_depth=m.max_depth)
+        W = O.make_weights(ocfg, seed=case["wseed"])
+        load_weights(model, W)
+        h, w, R = case["h"], case["w"], case["R"]
+        x = torch.randn(1, 256, h, w, generator=torch.Generator().manual_seed(case["xseed"]))
+        nseed = case["xseed"] + 1000
+        torch.manual_seed(nseed)
+        noise = torch.randn((R, 1, h, w))
+        steps = []
+        record_head(model, steps)
+        torch.manual_seed(nseed)
+        out = model.sample(x, None)
+        out = torch.clamp(out, min=model.decode_head.min_depth, max=model.decode_head.max_depth)
+        np.savez_compressed(
+            os.path.join(HERE, case["name"] + ".npz"),
+            task="depth", model_type=m.type, config=case["cfg"], timesteps=ocfg.timesteps, randsteps=R,
+            bit_scale=ocfg.bit_scale, min_depth=ocfg.min_depth, max_depth=ocfg.max_depth,
+            h=h, w=w, wseed=case["wseed"], xseed=case["xseed"], nseed=nseed,
+            x_checksum=checksum(x), noise_checksum=checksum(noise),
+            w_checksum=checksum(torch.cat([v.flatten() for _, v in sorted(W.items())])),
+            out=out.numpy(), step_depth=torch.stack(steps).numpy().astype(np.float32))
+        print(case["name"], tuple(out.shape), float(out.mean()), float(out.min()), float(out.max()))
+
+
+if __name__ == "__main__":
+    {"seg": run_seg, "depth": run_depth}[sys.argv[1]]()

@@ -1,0 +1,52 @@
+"""Helpers shared by the golden-fixture tests (regenerate inputs from stored seeds)."""
+import glob
+import os
+
+import numpy as np
+import torch
+
+from oracle import ddp_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_files(task=None):
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        if task is None or os.path.basename(f).startswith(task):
+            out.append(f)
+    return out
+
+
+def checksum(t):
+    t = t.double()
+    return np.array([float(t.sum()), float(t.abs().sum())])
+
+
+def load_case(path):
+    """-> (cfg, W, x (1,256,h,w), noise (1,R,Cin,h,w), golden dict)."""
+    g = dict(np.load(path, allow_pickle=False))
+    task = str(g["task"])
+    if task == "seg":
+        cfg = O.OracleConfig(task="seg", num_classes=int(g["num_classes"]), timesteps=int(g["timesteps"]),
+                             randsteps=int(g["randsteps"]), bit_scale=float(g["bit_scale"]),
+                             accumulation=bool(g["accumulation"]))
+        cin = 256
+    else:
+        cfg = O.OracleConfig(task="depth", timesteps=int(g["timesteps"]), randsteps=int(g["randsteps"]),
+                             bit_scale=float(g["bit_scale"]), min_depth=float(g["min_depth"]),
+                             max_depth=float(g["max_depth"]))
+        cin = 1
+    W = O.make_weights(cfg, seed=int(g["wseed"]))
+    h, w, R = int(g["h"]), int(g["w"]), cfg.randsteps
+    x = torch.randn(1, 256, h, w, generator=torch.Generator().manual_seed(int(g["xseed"])))
+    state = torch.get_rng_state()
+    torch.manual_seed(int(g["nseed"]))
+    noise = torch.randn((R, cin, h, w))[None]
+    torch.set_rng_state(state)
+    # the fixtures were produced from exactly these tensors
+    assert np.allclose(checksum(x), g["x_checksum"], rtol=0, atol=1e-6), "x regeneration drifted"
+    assert np.allclose(checksum(noise), g["noise_checksum"], rtol=0, atol=1e-6), "noise regeneration drifted"
+    wsum = checksum(torch.cat([v.flatten() for _, v in sorted(W.items())]))
+    assert np.allclose(wsum, g["w_checksum"], rtol=0, atol=1e-5), "weight regeneration drifted"
+    return cfg, W, x, noise, g
