@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the DDP reverse-diffusion decode loop on B200 (see DESIGN.md section d).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--gemm MODE]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle port) on host cores
+
+One "step" = one pass of the hot path (ddp_sample: T DDIM steps of the denoiser) over one batch of
+synthetic images already resident in HBM.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> task, classes, (h, w) tokens, T, R, accumulation, images per GPU, BASELINE.json config
+WORKLOADS = {
+    # BASELINE.json configs[2] (the config the metric "512x1024, T=10" is quoted on): 64 images on 8 GPUs = 8 per GPU
+    "cityscapes_512x1024_T10": dict(task="seg", C=19, h=128, w=256, T=10, R=1, acc=False, per_gpu=8, bit_scale=0.01),
+    "cityscapes_512x1024_T3": dict(task="seg", C=19, h=128, w=256, T=3, R=1, acc=False, per_gpu=8, bit_scale=0.01),
+    # configs[1]: Swin-T ADE20K 512x512, 150 classes, T=3 (accumulation=True in the ADE configs), batch 32 on 1 GPU
+    "ade_512x512_T3": dict(task="seg", C=150, h=128, w=128, T=3, R=1, acc=True, per_gpu=32, bit_scale=0.01),
+    # configs[3]: depth NYU 480x640, T=20, batch 32 on 4 GPUs = 8 per GPU
+    "nyu_480x640_T20": dict(task="depth", C=1, h=120, w=160, T=20, R=1, acc=False, per_gpu=8, bit_scale=0.1),
+    # configs[4]: uncertainty mode K=8 samples x T=10, batch 16 on 8 GPUs = 2 per GPU
+    "cityscapes_uncertainty_K8_T10": dict(task="seg", C=19, h=128, w=256, T=10, R=8, acc=False, per_gpu=2, bit_scale=0.01),
+    # configs[0]-sized smoke workload
+    "plumbing_64x64_T1": dict(task="seg", C=19, h=64, w=64, T=1, R=1, acc=False, per_gpu=1, bit_scale=0.01),
+}
+E, FFN = 256, 1024
+
+
+def flops_per_token_step(wl):
+    """Algorithmic GEMM FLOPs (multiply-add = 2), SURVEY.md section 8d."""
+    per_layer = 2 * E * (E + 64 + 32 + E) + 2 * 2 * E * FFN
+    if wl["task"] == "seg":
+        return 6 * per_layer + 2 * E * E + 2 * E * wl["C"]
+    return 6 * per_layer + 2 * E + 2 * E * 9
+
+
+def flops_per_image(wl):
+    n = wl["h"] * wl["w"]
+    return n * (wl["R"] * wl["T"] * flops_per_token_step(wl) + 2 * E * E)
+
+
+# algorithmic flops / bytes per token of one launch of each kernel class (fp32 activations in HBM)
+def class_cost(name, wl):
+    C = wl["C"]
+    table = {
+        "value_proj": (2 * E * E, 4 * (E + E)),
+        "sampling_proj": (2 * E * 96, 4 * (E + 96 + 96)),
+        "msda_gather": (2 * 8 * 4 * 4 * 32 + 0, 4 * (E + 96 + E)),
+        "out_proj_ln": (2 * E * E, 4 * (E + E + E)),
+        "ffn1_gelu": (2 * E * FFN, 4 * (E + FFN)),
+        "ffn2_ln_film": (2 * E * FFN, 4 * (FFN + E + E)),
+        "head_in": (2 * E * E, 4 * (E + E + E)),
+        "head_out": (2 * E * C, 4 * (E + C)),
+        "cond": (2 * E * E, 4 * (E + E)),
+        "step_update": (0, 4 * (C + 2 * E)),
+    }
+    return table.get(name, (0, 0))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained"),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_weights_and_inputs(wl, B, seed):
+    """Synthetic tensors of the named shapes: seeded CPU generator."""
+    from ddp_b200 import synthetic
+    W = synthetic.make_weights(task=wl["task"], num_classes=wl["C"], seed=7)
+    x, noise = synthetic.make_inputs(wl["task"], wl["R"], B, wl["h"], wl["w"], seed=seed)
+    return W, x, noise
+
+
+def oracle_cfg(wl):
+    from oracle import ddp_oracle as O       # cpu_baseline / --impl reference legs only
+    return O.OracleConfig(task=wl["task"], num_classes=wl["C"], timesteps=wl["T"], randsteps=wl["R"],
+                          accumulation=wl["acc"], bit_scale=wl["bit_scale"])
+
+
+def cpu_reference_step(cfg, W, x1, noise1, steps_sampled):
+    """One bounded sample of the reference's CPU path: 1 image, `steps_sampled` DDIM steps."""
+    from oracle import ddp_oracle as O
+    import dataclasses
+    c2 = dataclasses.replace(cfg, timesteps=steps_sampled)
+    t0 = time.perf_counter()
+    O.sample(W, c2, x1, noise1)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl, name):
+    """--impl reference: the reference's own PyTorch-CPU path (oracle port, pinned bit-for-bit to the
+    reference) on the host cores.  Each step = 1 image x 1 DDIM step; images/sec = 1 / (T * t_step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    W, x, noise = make_weights_and_inputs(wl, 1, seed=1234)
+    cfg = oracle_cfg(wl)
+    for _ in range(args.warmup):
+        cpu_reference_step(cfg, W, x, noise, 1)
+    ts = [cpu_reference_step(cfg, W, x, noise, 1) for _ in range(args.steps)]
+    t_step = sum(ts) / len(ts)
+    value = 1.0 / (wl["T"] * t_step)
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, name, 1, args),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"1 image x 1 of {wl['T']} DDIM steps per bench step, images/s = 1/(T*t_step)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, name, global_batch, args):
+    return {"workload": name, "task": wl["task"], "tokens": [wl["h"], wl["w"]], "classes": wl["C"],
+            "ddim_steps": wl["T"], "randsteps": wl["R"], "accumulation": wl["acc"], "global_batch": global_batch,
+            "images_per_gpu": wl["per_gpu"], "parallelism": f"dp{args.gpus} (images sharded, one NCCL gather of logits)",
+            "gemm_mode": args.gemm, "l2": "inputs larger than L2 (x alone is %.0f MB per rank)" %
+            (wl["per_gpu"] * E * wl["h"] * wl["w"] * 4 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cityscapes_512x1024_T10", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gemm", default=os.environ.get("DDP_GEMM", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-gpu", type=int, default=0, help="override images per GPU")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.per_gpu:
+        wl["per_gpu"] = args.per_gpu
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ddp_b200 import DecodeEngine
+    B = wl["per_gpu"]
+    W, x, noise = make_weights_and_inputs(wl, B, seed=1234 + rank)
+    eng = DecodeEngine(task=wl["task"], num_classes=wl["C"], timesteps=wl["T"], accumulation=wl["acc"],
+                       bit_scale=wl["bit_scale"], gemm_mode=args.gemm)
+    eng.load_state_dict(W)
+    xd, nd = x.to(dev), noise.to(dev)
+    xh, nh = x.pin_memory(), noise.pin_memory()
+    out_h = torch.empty((B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32).pin_memory()
+    gathered = None
+    if world > 1:
+        gathered = torch.empty((world * B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32, device=dev)
+
+    def step_device():
+        out = eng.sample(xd, nd)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)     # the single gather of final logits
+        return out
+
+    def step_e2e():
+        eng.sample_host(xh, nh, out=out_h)                  # H2D x+noise, loop, D2H logits: all inside
+        return out_h
+
+    def timed(fn, steps, sampler=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms, clocks
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    eng.profile(True)
+    ms, clocks = timed(step_device, args.steps, ClockSampler(local) if rank == 0 else None)
+    prof = eng.profile_collect()
+    eng.profile(False)
+    launches = eng.last_launch_count
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # end to end through the host-buffer entry point
+    step_e2e()
+    t0 = time.perf_counter()
+    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)))
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+    h2d = (xh.numel() + nh.numel()) * 4
+    d2h = out_h.numel() * 4
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    # dominant kernel class by device time
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    dname, (dms, dcount) = dom
+    tokens_per_launch = B * wl["R"] * wl["h"] * wl["w"]
+    fl, by = class_cost(dname, wl)
+    avg_s = dms / max(dcount, 1) / 1e3
+    gemm_like = dname not in ("msda_gather", "step_update", "finalize", "layout")
+    if gemm_like:
+        achieved = fl * tokens_per_launch / avg_s / 1e12
+        roof = {"bound": "tensor", "kernel": dname, "achieved": achieved, "peak": peaks["tensor_sustained"] or peaks["tensor"],
+                "unit": "TFLOP/s", "frac": achieved / (peaks["tensor_sustained"] or peaks["tensor"]),
+                "peak_source": peaks["source"] + " (bf16 dense, sustained)", "traffic": None}
+    else:
+        achieved = by * tokens_per_launch / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None}
+    roof["avg_launch_ms"] = 1e3 * avg_s
+    roof["launches_timed"] = dcount
+    total_prof = sum(v[0] for v in prof.values())
+    roof["share_of_step"] = dms / total_prof if total_prof else None
+    whole = world * B * args.steps * flops_per_image(wl) / (ms / 1e3) / 1e12
+    kernel_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        cfg = oracle_cfg(wl)
+        cpu_reference_step(cfg, W, x[:1], noise[:1], 1)            # warm-up (first-touch, thread pools)
+        nsteps = 2 if wl["h"] * wl["w"] >= 16384 else min(wl["T"], 4)
+        t = cpu_reference_step(cfg, W, x[:1], noise[:1], nsteps)
+        cpu_value = 1.0 / (t / nsteps * wl["T"])
+        cpu_baseline = {"value": cpu_value, "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": f"oracle (PyTorch-CPU port pinned to the reference), 1 image, {nsteps} of {wl['T']} "
+                                  f"DDIM steps in {t:.1f} s, scaled to T={wl['T']}"}
+
+    line = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else ("f32 via 3xfp16 tensor-core split" if args.gemm == "tc_3xf16" else "f16"),
+        "data": "synthetic", "config": workload_config(wl, args.workload, world * B, args),
+        "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": launches * args.steps, "launches_per_step": launches,
+        "roofline": roof, "whole_loop_tflops": whole, "kernel_ms_per_step": kernel_ms,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,775 @@
+// libddp_b200.so — C ABI + host orchestration of the B200-native DDP decode head (see include/ddp_b200.h).
+//
+// Host side: owns weights (repacked into kernel layouts), shape-only constants and the launch
+// sequence of the T-step sampling loop.  No torch, no CPU compute path: every tensor op is a kernel
+// in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ddp_b200.h"
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+using namespace ddp;
+
+namespace {
+
+struct WeightSpec {
+    std::string name;
+    int64_t numel;
+    std::vector<float> host;
+    bool set = false;
+    float* dev = nullptr;     // raw upload (reference layout)
+};
+
+struct LayerW {
+    float *Wv_t, *bv, *Ws_t, *bs, *Wo_t, *bo, *W1_t, *b1, *W2_t, *b2, *g1, *e1, *g2, *e2, *Wt, *bt;
+};
+
+struct Tap { int kind, step, layer; float* dst; };
+struct ProfRec { int tag; cudaEvent_t a, b; };
+struct Override { int step; const float* src; };
+
+}  // namespace
+
+struct ddp_handle {
+    ddp_config cfg;
+    int device = 0;
+    std::string err;
+    std::vector<WeightSpec> specs;
+    bool committed = false, planned = false;
+
+    // weights (device)
+    float* w_arena = nullptr;
+    float *Wx_t = nullptr, *Wm_t = nullptr, *wm_vec = nullptr, *b_tr = nullptr;
+    LayerW L[kMaxLayers];
+    float *Wout_t = nullptr, *b_out = nullptr;     // conv_seg (C cols) or conv_depth taps (9 cols)
+    float conv_depth_bias = 0.f;
+    float *t_w = nullptr, *t_W1 = nullptr, *t_b1 = nullptr, *t_W3 = nullptr, *t_b3 = nullptr;
+    float *emb = nullptr, *lut = nullptr;
+
+    // plan
+    int B = 0, R = 0, H = 0, W = 0, N = 0, rows = 0;
+    float* p_arena = nullptr;
+    float *pe = nullptr, *pew[kMaxLayers] = {nullptr};
+    float *d_time_in = nullptr, *four = nullptr, *h1 = nullptr, *temb = nullptr, *film = nullptr;
+    size_t ws_bytes = 0, ws_compute_bytes = 0;
+
+    // schedule (host)
+    std::vector<float> time_in, a_now, s_now, a_next, s_next;
+    bool sched_override = false, time_dirty = true;
+
+    std::vector<Tap> taps;
+    std::vector<Override> overrides;
+    int64_t launches = 0;
+
+    // per-kernel-class device timing (ddp_profile_*)
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+std::string g_create_err;
+
+int fail(ddp_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, DDP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Bump {
+    char* base; size_t off = 0;
+    explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+    float* take(size_t nfloats) {
+        float* p = reinterpret_cast<float*>(base + off);
+        off += align_up(nfloats * sizeof(float), 256);
+        return p;
+    }
+};
+
+void add_spec(ddp_handle* h, const std::string& name, int64_t numel) {
+    WeightSpec s;
+    s.name = name;
+    s.numel = numel;
+    h->specs.push_back(std::move(s));
+}
+
+WeightSpec* find_spec(ddp_handle* h, const std::string& name) {
+    for (auto& s : h->specs)
+        if (s.name == name) return &s;
+    return nullptr;
+}
+
+void build_specs(ddp_handle* h) {
+    const ddp_config& c = h->cfg;
+    const int fd = c.learned_sinusoidal_dim + 1;
+    if (c.task == DDP_TASK_SEG) {
+        add_spec(h, "embedding_table.weight", (int64_t)(c.num_classes + 1) * kE);
+        add_spec(h, "transform.conv.weight", (int64_t)kE * 2 * kE);
+        add_spec(h, "transform.conv.bias", kE);
+    } else {
+        add_spec(h, "down.conv.weight", (int64_t)kE * (kE + 1));
+        add_spec(h, "down.conv.bias", kE);
+    }
+    add_spec(h, "time_mlp.0.weights", c.learned_sinusoidal_dim / 2);
+    add_spec(h, "time_mlp.1.weight", (int64_t)kTimeDim * fd);
+    add_spec(h, "time_mlp.1.bias", kTimeDim);
+    add_spec(h, "time_mlp.3.weight", (int64_t)kTimeDim * kTimeDim);
+    add_spec(h, "time_mlp.3.bias", kTimeDim);
+    for (int j = 0; j < c.num_layers; ++j) {
+        std::string p = "decode_head.encoder.layers." + std::to_string(j) + ".";
+        add_spec(h, p + "attentions.0.sampling_offsets.weight", 64 * kE);
+        add_spec(h, p + "attentions.0.sampling_offsets.bias", 64);
+        add_spec(h, p + "attentions.0.attention_weights.weight", 32 * kE);
+        add_spec(h, p + "attentions.0.attention_weights.bias", 32);
+        add_spec(h, p + "attentions.0.value_proj.weight", kE * kE);
+        add_spec(h, p + "attentions.0.value_proj.bias", kE);
+        add_spec(h, p + "attentions.0.output_proj.weight", kE * kE);
+        add_spec(h, p + "attentions.0.output_proj.bias", kE);
+        add_spec(h, p + "time_mlp.1.weight", (int64_t)2 * kE * kTimeDim);
+        add_spec(h, p + "time_mlp.1.bias", 2 * kE);
+        add_spec(h, p + "ffns.0.layers.0.0.weight", (int64_t)kFFN * kE);
+        add_spec(h, p + "ffns.0.layers.0.0.bias", kFFN);
+        add_spec(h, p + "ffns.0.layers.1.weight", (int64_t)kE * kFFN);
+        add_spec(h, p + "ffns.0.layers.1.bias", kE);
+        add_spec(h, p + "norms.0.weight", kE);
+        add_spec(h, p + "norms.0.bias", kE);
+        add_spec(h, p + "norms.1.weight", kE);
+        add_spec(h, p + "norms.1.bias", kE);
+    }
+    if (c.task == DDP_TASK_SEG) {
+        add_spec(h, "decode_head.conv_seg.weight", (int64_t)c.num_classes * kE);
+        add_spec(h, "decode_head.conv_seg.bias", c.num_classes);
+    } else {
+        add_spec(h, "decode_head.conv_depth.weight", (int64_t)kE * 9);
+        add_spec(h, "decode_head.conv_depth.bias", 1);
+    }
+}
+
+// ---- default schedule: plain float math in the op order of the reference ----------------------
+float f_log_snr_cosine(float t) {   // ddp.py:22-24
+    volatile float a = t + 0.0002f;
+    a = a / 1.00025f;
+    a = a * 3.14159265358979323846f;
+    a = a * 0.5f;
+    volatile float c = cosf(a);
+    volatile float c2 = c * c;
+    volatile float v = 1.0f / c2;
+    v = v - 1.0f;
+    if (v < 1e-5f) v = 1e-5f;
+    return -logf(v);
+}
+float f_log_snr_linear(float t) {   // ddp.py:18-19
+    volatile float a = t * t;
+    a = 10.0f * a;
+    a = 1e-4f + a;
+    return -logf(expm1f(a));
+}
+float f_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+float f_gamma_depth(float t) {      // depth/depth/models/depther/ddp.py:207-208
+    volatile float a = t + 0.0002f;
+    a = a / 1.00025f;
+    a = a * 3.14159265358979323846f;
+    a = a / 2.0f;
+    volatile float c = cosf(a);
+    return c * c;
+}
+
+void default_schedule(ddp_handle* h) {
+    const ddp_config& c = h->cfg;
+    const int T = c.timesteps;
+    h->time_in.assign(T, 0.f); h->a_now.assign(T, 0.f); h->s_now.assign(T, 0.f);
+    h->a_next.assign(T, 0.f); h->s_next.assign(T, 0.f);
+    for (int step = 0; step < T; ++step) {
+        if (c.task == DDP_TASK_SEG) {
+            double s0 = (double)c.sample_range_lo;
+            double t_now = 1 - ((double)step / T) * (1 - s0);
+            double t_next = 1 - (double)(step + 1 + c.time_difference) / T * (1 - s0);
+            if (t_next < s0) t_next = s0;
+            float ln = c.noise_schedule == DDP_SCHEDULE_COSINE ? f_log_snr_cosine((float)t_now) : f_log_snr_linear((float)t_now);
+            float lx = c.noise_schedule == DDP_SCHEDULE_COSINE ? f_log_snr_cosine((float)t_next) : f_log_snr_linear((float)t_next);
+            h->time_in[step] = ln;
+            h->a_now[step] = sqrtf(f_sigmoid(ln));  h->s_now[step] = sqrtf(f_sigmoid(-ln));
+            h->a_next[step] = sqrtf(f_sigmoid(lx)); h->s_next[step] = sqrtf(f_sigmoid(-lx));
+        } else {
+            double t_now = 1 - (double)step / T;
+            double t_next = 1 - (double)(step + 1 + c.time_difference) / T;
+            if (t_next < 0) t_next = 0;
+            h->time_in[step] = (float)t_now;
+            h->a_now[step] = f_gamma_depth((float)t_now);
+            h->a_next[step] = f_gamma_depth((float)t_next);
+        }
+    }
+}
+
+cudaEvent_t prof_event(ddp_handle* h) {
+    if (!h->ev_pool.empty()) { cudaEvent_t e = h->ev_pool.back(); h->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+inline void prof_begin(ddp_handle* h, int tag, cudaStream_t st) {
+    if (!h->prof_on) return;
+    ProfRec r{tag, prof_event(h), prof_event(h)};
+    cudaEventRecord(r.a, st);
+    h->prof.push_back(r);
+}
+inline void prof_end(ddp_handle* h, cudaStream_t st) {
+    if (!h->prof_on) return;
+    cudaEventRecord(h->prof.back().b, st);
+}
+
+#define LAUNCH_CHECK(h)                                                                           \
+    do {                                                                                          \
+        (h)->launches++;                                                                          \
+        cudaError_t e_ = cudaGetLastError();                                                      \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, DDP_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+// KLAUNCH(tag, launch-expression): one kernel launch, counted, optionally timed per class
+#define KLAUNCH(h, tag, st, ...)          \
+    do {                                  \
+        prof_begin(h, tag, st);           \
+        __VA_ARGS__;                      \
+        prof_end(h, st);                  \
+        LAUNCH_CHECK(h);                  \
+    } while (0)
+
+int repack(ddp_handle* h, const float* src, int rows, int K, int row_stride, int k_stride, int off,
+           float* dst, int ld, int col0, cudaStream_t st) {
+    int total = rows * K;
+    k_repack_transposed<<<(total + 255) / 256, 256, 0, st>>>(src, rows, K, row_stride, k_stride, off, dst, ld, col0);
+    LAUNCH_CHECK(h);
+    return DDP_OK;
+}
+
+// time embeddings + FiLM vectors of all steps (data independent)
+int compute_time_constants(ddp_handle* h, cudaStream_t st) {
+    const ddp_config& c = h->cfg;
+    const int T = c.timesteps, Lc = c.num_layers;
+    const int fd = c.learned_sinusoidal_dim + 1;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_time_in, h->time_in.data(), T * sizeof(float), cudaMemcpyHostToDevice, st));
+    k_fourier<<<T, 32, 0, st>>>(h->d_time_in, h->t_w, c.learned_sinusoidal_dim / 2, h->four, T);
+    LAUNCH_CHECK(h);
+    dim3 g1((kTimeDim * 32 + 255) / 256, T);
+    k_gemv<0, 1><<<g1, 256, 0, st>>>(h->t_W1, h->t_b1, h->four, h->h1, kTimeDim, fd, fd, kTimeDim);
+    LAUNCH_CHECK(h);
+    k_gemv<0, 0><<<g1, 256, 0, st>>>(h->t_W3, h->t_b3, h->h1, h->temb, kTimeDim, kTimeDim, kTimeDim, kTimeDim);
+    LAUNCH_CHECK(h);
+    dim3 g2((2 * kE * 32 + 255) / 256, T);
+    for (int j = 0; j < Lc; ++j) {
+        k_gemv<1, 0><<<g2, 256, 0, st>>>(h->L[j].Wt, h->L[j].bt, h->temb, h->film + (size_t)j * 2 * kE,
+                                         2 * kE, kTimeDim, kTimeDim, Lc * 2 * kE);
+        LAUNCH_CHECK(h);
+    }
+    h->time_dirty = false;
+    return DDP_OK;
+}
+
+int do_tap(ddp_handle* h, int kind, int step, int layer, const float* src, size_t nfloats, cudaStream_t st) {
+    for (const Tap& t : h->taps) {
+        if (t.kind == kind && t.step == step && (t.layer == layer || layer < 0)) {
+            CUDA_TRY(h, cudaMemcpyAsync(t.dst, src, nfloats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return DDP_OK;
+}
+
+struct Workspace {
+    float *cond, *state, *q, *V, *samp, *g, *hid, *logits, *accum, *pred;
+    float *stage_x, *stage_noise, *stage_out;
+    int32_t* stage_cls;
+};
+
+size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_bytes) {
+    const ddp_config& c = h->cfg;
+    const size_t N = h->N, rows = h->rows, B = h->B;
+    const size_t cin = c.task == DDP_TASK_SEG ? kE : 1;
+    const size_t cout = c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 16;
+    Bump b(base);
+    Workspace w;
+    w.cond = b.take(B * N * kE);
+    w.state = b.take(rows * N * cin);
+    w.q = b.take(rows * N * kE);
+    w.V = b.take(rows * N * kE);
+    w.samp = b.take(rows * N * kSampW);
+    w.g = b.take(rows * N * kE);
+    w.hid = b.take(rows * N * kFFN);
+    w.logits = b.take(rows * N * cout);
+    w.accum = b.take(B * N * (c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1));
+    w.pred = b.take(rows * N);
+    if (compute_bytes) *compute_bytes = b.off;
+    w.stage_x = b.take(B * kE * N);
+    w.stage_noise = b.take(rows * cin * N);
+    w.stage_out = b.take(B * (c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1) * N);
+    w.stage_cls = reinterpret_cast<int32_t*>(b.take(B * N));
+    if (ws) *ws = w;
+    return b.off;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int ddp_abi_version(void) { return DDP_ABI_VERSION; }
+
+const char* ddp_last_error(const ddp_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int ddp_create(const ddp_config* cfg, ddp_handle** out) {
+    if (!cfg || !out) return fail(nullptr, DDP_ERR_INVALID, "ddp_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DDP_ABI_VERSION)
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: abi_version %d != %d", cfg->abi_version, DDP_ABI_VERSION);
+    if (cfg->task != DDP_TASK_SEG && cfg->task != DDP_TASK_DEPTH)
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: invalid task %d", cfg->task);
+    if (cfg->task == DDP_TASK_SEG && (cfg->num_classes < 1 || cfg->num_classes > 256))
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: num_classes %d outside [1, 256]", cfg->num_classes);
+    if (cfg->timesteps < 1 || cfg->timesteps > kMaxSteps)
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: timesteps %d outside [1, %d]", cfg->timesteps, kMaxSteps);
+    if (cfg->num_layers < 1 || cfg->num_layers > kMaxLayers)
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: num_layers %d outside [1, %d]", cfg->num_layers, kMaxLayers);
+    if (cfg->learned_sinusoidal_dim < 2 || cfg->learned_sinusoidal_dim > 30 || (cfg->learned_sinusoidal_dim & 1))
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: learned_sinusoidal_dim must be even and in [2, 30]");
+    if (cfg->noise_schedule != DDP_SCHEDULE_COSINE && cfg->noise_schedule != DDP_SCHEDULE_LINEAR)
+        return fail(nullptr, DDP_ERR_INVALID, "invalid noise schedule %d", cfg->noise_schedule);   // ddp.py:90 ValueError
+    if (cfg->diffusion != DDP_DIFFUSION_DDIM)
+        return fail(nullptr, DDP_ERR_UNSUPPORTED, "diffusion %d: only ddim is built", cfg->diffusion);   // ddp.py:123
+    if (cfg->gemm_mode != DDP_GEMM_FP32)
+        return fail(nullptr, DDP_ERR_UNSUPPORTED, "gemm_mode %d not built in this library", cfg->gemm_mode);
+    if (cfg->task == DDP_TASK_DEPTH && !(cfg->max_depth > cfg->min_depth))
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: max_depth must exceed min_depth");
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail(nullptr, DDP_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(nullptr, DDP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, DDP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                    prop.major, prop.minor);
+    ddp_handle* h = new ddp_handle();
+    h->cfg = *cfg;
+    h->device = dev;
+    build_specs(h);
+    default_schedule(h);
+    *out = h;
+    return DDP_OK;
+}
+
+void ddp_destroy(ddp_handle* h) {
+    if (!h) return;
+    for (auto& s : h->specs)
+        if (s.dev) cudaFree(s.dev);
+    for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto& e : h->ev_pool) cudaEventDestroy(e);
+    if (h->w_arena) cudaFree(h->w_arena);
+    if (h->p_arena) cudaFree(h->p_arena);
+    delete h;
+}
+
+int ddp_weight_count(const ddp_handle* h) { return h ? (int)h->specs.size() : 0; }
+
+const char* ddp_weight_name(const ddp_handle* h, int index, int64_t* numel) {
+    if (!h || index < 0 || index >= (int)h->specs.size()) return nullptr;
+    if (numel) *numel = h->specs[index].numel;
+    return h->specs[index].name.c_str();
+}
+
+int ddp_set_weight(ddp_handle* h, const char* name, const float* host_data, int64_t numel) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!name || !host_data) return fail(h, DDP_ERR_INVALID, "ddp_set_weight: null argument");
+    WeightSpec* s = find_spec(h, name);
+    if (!s) return fail(h, DDP_ERR_WEIGHT, "ddp_set_weight: '%s' is not a hot-path weight", name);
+    if (s->numel != numel)
+        return fail(h, DDP_ERR_WEIGHT, "ddp_set_weight: '%s' expects %lld elements, got %lld", name,
+                    (long long)s->numel, (long long)numel);
+    s->host.assign(host_data, host_data + numel);
+    s->set = true;
+    h->committed = false;
+    return DDP_OK;
+}
+
+int ddp_commit_weights(ddp_handle* h) {
+    if (!h) return DDP_ERR_INVALID;
+    for (auto& s : h->specs)
+        if (!s.set) return fail(h, DDP_ERR_WEIGHT, "ddp_commit_weights: '%s' was never set", s.name.c_str());
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const ddp_config& c = h->cfg;
+    cudaStream_t st = 0;
+    for (auto& s : h->specs) {
+        if (!s.dev) CUDA_TRY(h, cudaMalloc(&s.dev, align_up(s.numel * sizeof(float), 256)));
+        CUDA_TRY(h, cudaMemcpy(s.dev, s.host.data(), s.numel * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    auto dev = [&](const std::string& n) { return find_spec(h, n)->dev; };
+    // arena for the repacked (transposed, padded) matrices
+    const int Lc = c.num_layers;
+    size_t fl = 0;
+    auto need = [&](size_t n) { fl += align_up(n * sizeof(float), 256) / sizeof(float); };
+    need(kE * kE); need(kE * kE); need(kE);            // Wx_t, Wm_t, wm_vec
+    for (int j = 0; j < Lc; ++j) { need(kE * kE); need(kE * 128); need(128); need(kE * kE); need(kE * kFFN); need(kFFN * kE); }
+    need(kE * 256);                                    // Wout_t
+    need(256);                                         // b_out padded
+    need((size_t)(c.num_classes + 1) * kE);            // lut
+    if (h->w_arena) { cudaFree(h->w_arena); h->w_arena = nullptr; }
+    CUDA_TRY(h, cudaMalloc(&h->w_arena, fl * sizeof(float)));
+    CUDA_TRY(h, cudaMemset(h->w_arena, 0, fl * sizeof(float)));
+    Bump b(h->w_arena);
+    h->Wx_t = b.take(kE * kE); h->Wm_t = b.take(kE * kE); h->wm_vec = b.take(kE);
+    int rc;
+    if (c.task == DDP_TASK_SEG) {
+        const float* tw = dev("transform.conv.weight");          // (256, 512): [o][i]
+        if ((rc = repack(h, tw, kE, kE, 2 * kE, 1, 0, h->Wx_t, kE, 0, st))) return rc;
+        if ((rc = repack(h, tw, kE, kE, 2 * kE, 1, kE, h->Wm_t, kE, 0, st))) return rc;
+        h->b_tr = dev("transform.conv.bias");
+    } else {
+        const float* tw = dev("down.conv.weight");               // (256, 257)
+        if ((rc = repack(h, tw, kE, kE, kE + 1, 1, 0, h->Wx_t, kE, 0, st))) return rc;
+        if ((rc = repack(h, tw, kE, 1, kE + 1, 1, kE, h->wm_vec, kE, 0, st))) return rc;
+        h->b_tr = dev("down.conv.bias");
+    }
+    for (int j = 0; j < Lc; ++j) {
+        std::string p = "decode_head.encoder.layers." + std::to_string(j) + ".";
+        LayerW& L = h->L[j];
+        L.Wv_t = b.take(kE * kE); L.Ws_t = b.take(kE * 128); L.bs = b.take(128);
+        L.Wo_t = b.take(kE * kE); L.W1_t = b.take(kE * kFFN); L.W2_t = b.take(kFFN * kE);
+        if ((rc = repack(h, dev(p + "attentions.0.value_proj.weight"), kE, kE, kE, 1, 0, L.Wv_t, kE, 0, st))) return rc;
+        if ((rc = repack(h, dev(p + "attentions.0.sampling_offsets.weight"), 64, kE, kE, 1, 0, L.Ws_t, 128, 0, st))) return rc;
+        if ((rc = repack(h, dev(p + "attentions.0.attention_weights.weight"), 32, kE, kE, 1, 0, L.Ws_t, 128, 64, st))) return rc;
+        CUDA_TRY(h, cudaMemcpy(L.bs, dev(p + "attentions.0.sampling_offsets.bias"), 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+        CUDA_TRY(h, cudaMemcpy(L.bs + 64, dev(p + "attentions.0.attention_weights.bias"), 32 * sizeof(float), cudaMemcpyDeviceToDevice));
+        if ((rc = repack(h, dev(p + "attentions.0.output_proj.weight"), kE, kE, kE, 1, 0, L.Wo_t, kE, 0, st))) return rc;
+        if ((rc = repack(h, dev(p + "ffns.0.layers.0.0.weight"), kFFN, kE, kE, 1, 0, L.W1_t, kFFN, 0, st))) return rc;
+        if ((rc = repack(h, dev(p + "ffns.0.layers.1.weight"), kE, kFFN, kFFN, 1, 0, L.W2_t, kE, 0, st))) return rc;
+        L.bv = dev(p + "attentions.0.value_proj.bias");
+        L.bo = dev(p + "attentions.0.output_proj.bias");
+        L.b1 = dev(p + "ffns.0.layers.0.0.bias");
+        L.b2 = dev(p + "ffns.0.layers.1.bias");
+        L.g1 = dev(p + "norms.0.weight"); L.e1 = dev(p + "norms.0.bias");
+        L.g2 = dev(p + "norms.1.weight"); L.e2 = dev(p + "norms.1.bias");
+        L.Wt = dev(p + "time_mlp.1.weight"); L.bt = dev(p + "time_mlp.1.bias");
+    }
+    h->Wout_t = b.take(kE * 256);
+    h->b_out = b.take(256);
+    h->lut = b.take((size_t)(c.num_classes + 1) * kE);
+    if (c.task == DDP_TASK_SEG) {
+        if ((rc = repack(h, dev("decode_head.conv_seg.weight"), c.num_classes, kE, kE, 1, 0, h->Wout_t, 256, 0, st))) return rc;
+        CUDA_TRY(h, cudaMemcpy(h->b_out, dev("decode_head.conv_seg.bias"), c.num_classes * sizeof(float), cudaMemcpyDeviceToDevice));
+        h->emb = dev("embedding_table.weight");
+        int n = (c.num_classes + 1) * kE;
+        k_embed_lut<<<(n + 255) / 256, 256, 0, st>>>(h->emb, h->lut, n, c.bit_scale);
+        LAUNCH_CHECK(h);
+    } else {
+        // conv_depth.weight (1, 256, 3, 3): tap t = kh*3+kw -> column t; element (c, t) at c*9 + t
+        if ((rc = repack(h, dev("decode_head.conv_depth.weight"), 9, kE, 1, 9, 0, h->Wout_t, 256, 0, st))) return rc;
+        h->conv_depth_bias = find_spec(h, "decode_head.conv_depth.bias")->host[0];
+    }
+    h->t_w = dev("time_mlp.0.weights");
+    h->t_W1 = dev("time_mlp.1.weight"); h->t_b1 = dev("time_mlp.1.bias");
+    h->t_W3 = dev("time_mlp.3.weight"); h->t_b3 = dev("time_mlp.3.bias");
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->committed = true;
+    h->planned = false;
+    return DDP_OK;
+}
+
+int ddp_set_schedule(ddp_handle* h, int timesteps, const float* time_in, const float* a_now, const float* s_now,
+                     const float* a_next, const float* s_next) {
+    if (!h) return DDP_ERR_INVALID;
+    if (timesteps != h->cfg.timesteps)
+        return fail(h, DDP_ERR_INVALID, "ddp_set_schedule: %d steps given, handle has %d", timesteps, h->cfg.timesteps);
+    if (!time_in || !a_now || !a_next) return fail(h, DDP_ERR_INVALID, "ddp_set_schedule: null array");
+    if (h->cfg.task == DDP_TASK_SEG && (!s_now || !s_next)) return fail(h, DDP_ERR_INVALID, "ddp_set_schedule: seg needs sigma arrays");
+    h->time_in.assign(time_in, time_in + timesteps);
+    h->a_now.assign(a_now, a_now + timesteps);
+    h->a_next.assign(a_next, a_next + timesteps);
+    if (s_now) h->s_now.assign(s_now, s_now + timesteps);
+    if (s_next) h->s_next.assign(s_next, s_next + timesteps);
+    h->sched_override = true;
+    h->time_dirty = true;
+    return DDP_OK;
+}
+
+int ddp_get_schedule(const ddp_handle* h, float* time_in, float* a_now, float* s_now, float* a_next, float* s_next) {
+    if (!h) return DDP_ERR_INVALID;
+    const int T = h->cfg.timesteps;
+    if (time_in) memcpy(time_in, h->time_in.data(), T * sizeof(float));
+    if (a_now) memcpy(a_now, h->a_now.data(), T * sizeof(float));
+    if (s_now) memcpy(s_now, h->s_now.data(), T * sizeof(float));
+    if (a_next) memcpy(a_next, h->a_next.data(), T * sizeof(float));
+    if (s_next) memcpy(s_next, h->s_next.data(), T * sizeof(float));
+    return DDP_OK;
+}
+
+int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspace_bytes) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->committed) return fail(h, DDP_ERR_STATE, "ddp_plan: call ddp_commit_weights first");
+    if (B < 1 || R < 1 || height < 1 || width < 1) return fail(h, DDP_ERR_INVALID, "ddp_plan: B, R, h, w must be >= 1");
+    if ((long long)B * R * height * width > (1ll << 30)) return fail(h, DDP_ERR_INVALID, "ddp_plan: too many tokens");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const ddp_config& c = h->cfg;
+    const int T = c.timesteps, Lc = c.num_layers, N = height * width;
+    h->B = B; h->R = R; h->H = height; h->W = width; h->N = N; h->rows = B * R;
+    if (h->p_arena) { cudaFree(h->p_arena); h->p_arena = nullptr; }
+    size_t fl = 0;
+    auto need = [&](size_t n) { fl += align_up(n * sizeof(float), 256) / sizeof(float); };
+    need((size_t)N * kE);
+    for (int j = 0; j < Lc; ++j) need((size_t)N * kSampW);
+    need(T); need((size_t)T * 32); need((size_t)T * kTimeDim); need((size_t)T * kTimeDim); need((size_t)T * Lc * 2 * kE);
+    CUDA_TRY(h, cudaMalloc(&h->p_arena, fl * sizeof(float)));
+    Bump b(h->p_arena);
+    h->pe = b.take((size_t)N * kE);
+    for (int j = 0; j < Lc; ++j) h->pew[j] = b.take((size_t)N * kSampW);
+    h->d_time_in = b.take(T); h->four = b.take((size_t)T * 32);
+    h->h1 = b.take((size_t)T * kTimeDim); h->temb = b.take((size_t)T * kTimeDim);
+    h->film = b.take((size_t)T * Lc * 2 * kE);
+    cudaStream_t st = 0;
+    k_sine_pe<<<(N * kE + 255) / 256, 256, 0, st>>>(h->pe, height, width);
+    LAUNCH_CHECK(h);
+    for (int j = 0; j < Lc; ++j) {
+        // pew_j = PE * [W_off | W_attn]^T + [b_off | b_attn]   (shape-only half of the (q + pos) projections)
+        EpiBias epi{h->pew[j], h->L[j].bs, kSampW, kSampW, N};
+        launch_gemm_simt<128, false>(h->pe, kE, 0, h->L[j].Ws_t, 128, N, kE, 128, epi, st);
+        LAUNCH_CHECK(h);
+    }
+    int rc = compute_time_constants(h, st);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->ws_bytes = carve(h, nullptr, nullptr, &h->ws_compute_bytes);
+    if (workspace_bytes) *workspace_bytes = h->ws_bytes;
+    h->planned = true;
+    return DDP_OK;
+}
+
+int ddp_add_tap(ddp_handle* h, int kind, int step, int layer, float* device_dst) {
+    if (!h || !device_dst) return DDP_ERR_INVALID;
+    if (kind < DDP_TAP_HEAD_IN || kind > DDP_TAP_FILM) return fail(h, DDP_ERR_INVALID, "ddp_add_tap: bad kind %d", kind);
+    if (step < 0 || step >= h->cfg.timesteps) return fail(h, DDP_ERR_INVALID, "ddp_add_tap: bad step %d", step);
+    h->taps.push_back(Tap{kind, step, layer, device_dst});
+    return DDP_OK;
+}
+
+int ddp_set_state_override(ddp_handle* h, int step, const float* device_state) {
+    if (!h || !device_state) return DDP_ERR_INVALID;
+    if (step < 0 || step >= h->cfg.timesteps) return fail(h, DDP_ERR_INVALID, "ddp_set_state_override: bad step %d", step);
+    h->overrides.push_back(Override{step, device_state});
+    return DDP_OK;
+}
+
+int ddp_clear_debug(ddp_handle* h) {
+    if (!h) return DDP_ERR_INVALID;
+    h->taps.clear();
+    h->overrides.clear();
+    return DDP_OK;
+}
+
+int64_t ddp_last_launch_count(const ddp_handle* h) { return h ? h->launches : 0; }
+
+static int load_state(ddp_handle* h, const float* src_nchw, float* state, cudaStream_t st) {
+    const int N = h->N, rows = h->rows;
+    if (h->cfg.task == DDP_TASK_SEG) {
+        dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
+        KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(src_nchw, state, kE, N)));
+    } else {
+        CUDA_TRY(h, cudaMemcpyAsync(state, src_nchw, (size_t)rows * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return DDP_OK;
+}
+
+int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
+               size_t workspace_bytes, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_sample: call ddp_plan first");
+    if (!x || !noise || !out || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_sample: null pointer");
+    if (workspace_bytes < h->ws_compute_bytes)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample: workspace %zu < required %zu", workspace_bytes, h->ws_compute_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ddp_config& c = h->cfg;
+    const int T = c.timesteps, Lc = c.num_layers, N = h->N, rows = h->rows, B = h->B, R = h->R;
+    const int M = rows * N;                       // tokens in flight
+    const bool seg = c.task == DDP_TASK_SEG;
+    const int C = seg ? c.num_classes : 1;
+    h->launches = 0;
+    int rc;
+    if (h->time_dirty && (rc = compute_time_constants(h, st))) return rc;
+    Workspace ws;
+    carve(h, workspace, &ws, nullptr);
+
+    // cond = W_x x + b: the step-invariant half of transform / down (x is read once, reused for all T steps)
+    {
+        EpiBias epi{ws.cond, h->b_tr, kE, kE, B * N};
+        KLAUNCH(h, DDP_K_COND, st, (launch_gemm_simt<256, true>(x, 0, N, h->Wx_t, kE, B * N, kE, kE, epi, st)));
+    }
+    if ((rc = load_state(h, noise, ws.state, st))) return rc;
+    if (seg) CUDA_TRY(h, cudaMemsetAsync(ws.accum, 0, (size_t)B * N * C * sizeof(float), st));
+
+    for (int k = 0; k < T; ++k) {
+        for (const Override& o : h->overrides)
+            if (o.step == k && (rc = load_state(h, o.src, ws.state, st))) return rc;
+        // head input tokens q = cond + W_m m_t
+        if (seg) {
+            EpiAddCond epi{ws.q, ws.cond, N, R, M};
+            KLAUNCH(h, DDP_K_HEAD_IN, st, (launch_gemm_simt<256, false>(ws.state, kE, 0, h->Wm_t, kE, M, kE, kE, epi, st)));
+        } else {
+            size_t n4 = (size_t)M * (kE / 4);
+            KLAUNCH(h, DDP_K_HEAD_IN, st,
+                    (k_depth_head_in<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws.cond, h->wm_vec, ws.state, ws.q, N, R, M)));
+        }
+        if ((rc = do_tap(h, DDP_TAP_HEAD_IN, k, -1, ws.q, (size_t)M * kE, st))) return rc;
+        if ((rc = do_tap(h, DDP_TAP_TEMB, k, -1, h->temb + (size_t)k * kTimeDim, kTimeDim, st))) return rc;
+
+        for (int j = 0; j < Lc; ++j) {
+            const LayerW& L = h->L[j];
+            const float* film = h->film + ((size_t)k * Lc + j) * 2 * kE;
+            {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
+                EpiBias epi{ws.V, L.bv, kE, kE, M};
+                KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
+            }
+            {   // offsets / attention weights = proj(q + pos) = q W^T + pew
+                EpiSampling epi{ws.samp, h->pew[j], N, M};
+                KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
+            }
+            if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
+            if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
+            KLAUNCH(h, DDP_K_GATHER, st,
+                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.samp, ws.g, h->H, h->W, M)));
+            if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
+            {   // q = LN1(q + output_proj(g))
+                EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
+                KLAUNCH(h, DDP_K_OUT_PROJ, st, (launch_gemm_simt<256, false>(ws.g, kE, 0, L.Wo_t, kE, M, kE, kE, epi, st)));
+            }
+            if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+            {   // hid = gelu(q W1^T + b1)
+                EpiGelu epi{ws.hid, L.b1, kFFN, M};
+                KLAUNCH(h, DDP_K_FFN1, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.W1_t, kFFN, M, kE, kFFN, epi, st)));
+            }
+            {   // q = FiLM(LN2(q + hid W2^T + b2))
+                EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
+                KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
+            }
+            if ((rc = do_tap(h, DDP_TAP_LAYER_OUT, k, j, ws.q, (size_t)M * kE, st))) return rc;
+            if ((rc = do_tap(h, DDP_TAP_FILM, k, j, film, 2 * kE, st))) return rc;
+        }
+
+        const bool last = (k == T - 1);
+        if (seg) {
+            EpiBias epi{ws.logits, h->b_out, C, C, M};
+            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 256, epi, st)));
+            if ((rc = do_tap(h, DDP_TAP_LOGITS, k, -1, ws.logits, (size_t)M * C, st))) return rc;
+            SegStepParams p;
+            p.logits = ws.logits; p.state = ws.state; p.accum = ws.accum; p.lut = h->lut;
+            p.N = N; p.R = R; p.C = C; p.B = B;
+            p.alpha = h->a_now[k]; p.sigma = h->s_now[k]; p.alpha_next = h->a_next[k]; p.sigma_next = h->s_next[k];
+            p.accumulate_prob = c.accumulation ? 1 : 0;
+            p.add_logits = (!c.accumulation && last) ? 1 : 0;
+            KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
+        } else {
+            EpiBias epi{ws.logits, nullptr, 16, 9, M};
+            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 128, epi, st)));
+            DepthStepParams p;
+            p.taps = ws.logits; p.state = ws.state; p.pred = ws.pred; p.out = out;
+            p.H = h->H; p.W = h->W; p.R = R; p.B = B;
+            p.conv_bias = h->conv_depth_bias; p.min_depth = c.min_depth; p.max_depth = c.max_depth; p.bit_scale = c.bit_scale;
+            p.gamma_now = h->a_now[k]; p.gamma_next = h->a_next[k];
+            p.last = last ? 1 : 0;
+            KLAUNCH(h, DDP_K_STEP, st, (k_depth_step<<<(B * N + 255) / 256, 256, 0, st>>>(p)));
+            if ((rc = do_tap(h, DDP_TAP_LOGITS, k, -1, ws.pred, (size_t)M, st))) return rc;
+        }
+        if ((rc = do_tap(h, DDP_TAP_STATE, k, -1, ws.state, (size_t)M * (seg ? kE : 1), st))) return rc;
+    }
+    if (seg) {
+        float count = c.accumulation ? (float)(T * R) : (float)R;
+        dim3 grid((N + 31) / 32, (C + 31) / 32, B), block(32, 8);
+        KLAUNCH(h, DDP_K_FINALIZE, st, (k_seg_finalize<<<grid, block, 0, st>>>(ws.accum, out, cls, N, C, count)));
+    }
+    return DDP_OK;
+}
+
+int ddp_profile_enable(ddp_handle* h, int on) {
+    if (!h) return DDP_ERR_INVALID;
+    h->prof_on = on != 0;
+    for (auto& r : h->prof) { h->ev_pool.push_back(r.a); h->ev_pool.push_back(r.b); }
+    h->prof.clear();
+    return DDP_OK;
+}
+
+int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_class, int n_classes) {
+    if (!h || !ms_by_class || !launches_by_class) return DDP_ERR_INVALID;
+    if (n_classes < DDP_K_COUNT) return fail(h, DDP_ERR_INVALID, "ddp_profile_collect: need %d classes", DDP_K_COUNT);
+    for (int i = 0; i < n_classes; ++i) { ms_by_class[i] = 0.f; launches_by_class[i] = 0; }
+    for (auto& r : h->prof) {
+        CUDA_TRY(h, cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_by_class[r.tag] += ms;
+        launches_by_class[r.tag] += 1;
+        h->ev_pool.push_back(r.a);
+        h->ev_pool.push_back(r.b);
+    }
+    h->prof.clear();
+    return DDP_OK;
+}
+
+const char* ddp_kernel_class_name(int cls) {
+    static const char* names[DDP_K_COUNT] = {"cond", "head_in", "value_proj", "sampling_proj", "msda_gather", "out_proj_ln",
+                                             "ffn1_gelu", "ffn2_ln_film", "head_out", "step_update", "finalize", "layout"};
+    return (cls >= 0 && cls < DDP_K_COUNT) ? names[cls] : nullptr;
+}
+
+int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_sample_host: call ddp_plan first");
+    if (!x_host || !noise_host || !out_host || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_sample_host: null pointer");
+    if (workspace_bytes < h->ws_bytes)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host: workspace %zu < required %zu", workspace_bytes, h->ws_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ddp_config& c = h->cfg;
+    const bool seg = c.task == DDP_TASK_SEG;
+    const size_t N = h->N, B = h->B, rows = h->rows;
+    const size_t cin = seg ? kE : 1, cout = seg ? (size_t)c.num_classes : 1;
+    Workspace ws;
+    carve(h, workspace, &ws, nullptr);
+    CUDA_TRY(h, cudaMemcpyAsync(ws.stage_x, x_host, B * kE * N * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(ws.stage_noise, noise_host, rows * cin * N * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = ddp_sample(h, ws.stage_x, ws.stage_noise, ws.stage_out, (seg && cls_host) ? ws.stage_cls : nullptr, workspace,
+                        workspace_bytes, stream);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out_host, ws.stage_out, B * cout * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (seg && cls_host)
+        CUDA_TRY(h, cudaMemcpyAsync(cls_host, ws.stage_cls, B * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return DDP_OK;
+}
+
+}  // extern "C"

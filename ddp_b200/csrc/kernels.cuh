@@ -1,0 +1,381 @@
+// Non-GEMM kernels of the DDP decode head: deformable gather, step epilogues (argmax -> embedding
+// LUT -> DDIM update, softmax accumulation), positional encoding, time embeddings, layout changes.
+#pragma once
+#include "common.cuh"
+
+namespace ddp {
+
+// ------------------------------------------------------------------------------------------------
+// layout changes
+// ------------------------------------------------------------------------------------------------
+// src [imgs][C][N] (NCHW) -> dst [imgs][N][C] (token-major).  32x32 smem tiles.
+__global__ void k_nchw_to_tokens(const float* __restrict__ src, float* __restrict__ dst, int C, int N) {
+    __shared__ float tile[32][33];
+    int img = blockIdx.z;
+    int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* s = src + (size_t)img * C * N;
+    float* d = dst + (size_t)img * C * N;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, n = n0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && n < N) ? s[(size_t)c * N + n] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int n = n0 + i, c = c0 + threadIdx.x;
+        if (n < N && c < C) d[(size_t)n * C + c] = tile[threadIdx.x][i];
+    }
+}
+
+// src [rows_in][K] -> dst [K][ld] with dst[k][col0 + r] = src[r][k*src_kstride + k_off] (weights repack);
+// generic strided gather so that conv weights (O, I, kh, kw) can be sliced.
+__global__ void k_repack_transposed(const float* __restrict__ src, int rows, int K, int src_row_stride,
+                                    int src_k_stride, int src_off, float* __restrict__ dst, int ld, int col0) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * K) return;
+    int r = idx % rows, k = idx / rows;
+    dst[(size_t)k * ld + col0 + r] = src[(size_t)r * src_row_stride + (size_t)k * src_k_stride + src_off];
+}
+
+// ------------------------------------------------------------------------------------------------
+// shape-only constants
+// ------------------------------------------------------------------------------------------------
+// SinePositionalEncoding(num_feats=128, normalize=True, offset=-0.5, scale=2*pi, temperature=10000, eps=1e-6)
+// segmentation/mmseg/models/utils/transformer.py:78-113, evaluated with the same fp32 op order.
+// pe [N][256], channel = [pos_y(128) | pos_x(128)], pos[2k] = sin, pos[2k+1] = cos.
+__global__ void k_sine_pe(float* __restrict__ pe, int H, int W) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int N = H * W;
+    if (idx >= N * kE) return;
+    int c = idx % kE, n = idx / kE;
+    int i = n / W, j = n % W;
+    const float scale = 6.283185307179586f;
+    float embed;
+    int k;
+    if (c < 128) {
+        embed = __fmul_rn(__fdiv_rn((float)(i + 1) - 0.5f, __fadd_rn((float)H, 1e-6f)), scale);
+        k = c;
+    } else {
+        embed = __fmul_rn(__fdiv_rn((float)(j + 1) - 0.5f, __fadd_rn((float)W, 1e-6f)), scale);
+        k = c - 128;
+    }
+    float expo = (float)(2 * (k / 2)) / 128.0f;
+    float dim_t = powf(10000.0f, expo);
+    float v = __fdiv_rn(embed, dim_t);
+    pe[idx] = (k & 1) ? cosf(v) : sinf(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embeddings (data independent: computed once per plan for all T steps)
+// ------------------------------------------------------------------------------------------------
+// LearnedSinusoidalPosEmb, segmentation/mmseg/models/segmentors/ddp.py:31-46: [l, sin(l w 2pi), cos(l w 2pi)]
+__global__ void k_fourier(const float* __restrict__ time_in, const float* __restrict__ w, int half,
+                          float* __restrict__ out, int T) {
+    int t = blockIdx.x;
+    int i = threadIdx.x;
+    int width = 2 * half + 1;
+    if (t >= T || i >= width) return;
+    float l = time_in[t];
+    float v;
+    if (i == 0) v = l;
+    else {
+        int k = (i - 1) % half;
+        float f = __fmul_rn(__fmul_rn(__fmul_rn(l, w[k]), 2.0f), 3.14159265358979323846f);
+        v = (i - 1 < half) ? sinf(f) : cosf(f);
+    }
+    out[t * width + i] = v;
+}
+
+// y[t][i] = act_out( sum_k W[i][k] * act_in(x[t][k]) + b[i] );  one warp per (i, t)
+template <int ACT_IN /*0 none, 1 silu*/, int ACT_OUT /*0 none, 1 gelu*/>
+__global__ void k_gemv(const float* __restrict__ Wm, const float* __restrict__ b, const float* __restrict__ x,
+                       float* __restrict__ y, int rows, int K, int x_stride, int y_stride) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int t = blockIdx.y;
+    if (warp >= rows) return;
+    const float* wr = Wm + (size_t)warp * K;
+    const float* xr = x + (size_t)t * x_stride;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float xv = xr[k];
+        if (ACT_IN == 1) xv = silu(xv);
+        s = fmaf(wr[k], xv, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        s += b[warp];
+        if (ACT_OUT == 1) s = gelu_erf(s);
+        y[(size_t)t * y_stride + warp] = s;
+    }
+}
+
+// (sigmoid(E[c]) * 2 - 1) * bit_scale    segmentation/mmseg/models/segmentors/ddp.py:236-237
+__global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ lut, int n, float bit_scale) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    float s = sigmoidf_(emb[idx]);
+    lut[idx] = __fmul_rn(__fadd_rn(__fmul_rn(s, 2.0f), -1.0f), bit_scale);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-scale deformable attention gather (1 level, 8 heads x 4 points, head dim 32)
+// ------------------------------------------------------------------------------------------------
+// out[row][n][32m + d] = sum_p a[n,m,p] * bilinear0( V[row][.][32m + d] at (x, y) )
+// with the reference's coordinate chain evaluated op by op in fp32:
+//   ref = (j + .5) / W                  deformable_head_with_time.py:76-84
+//   loc = ref + off / W                 vmmcv/ops/multi_scale_deform_attn.py:329-334
+//   grid = 2 loc - 1                    :121
+//   x = (grid + 1) * (W / 2) - .5       F.grid_sample(align_corners=False) unnormalisation
+// zero padding outside the map.  One warp per token: lane = (head = lane / 4, 8 channels).
+__global__ void __launch_bounds__(256)
+k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float* __restrict__ out,
+              int H, int W, int total_tokens) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= total_tokens) return;
+    int lane = threadIdx.x & 31;
+    int N = H * W;
+    int row = warp / N, n = warp - row * N;
+    int i = n / W, j = n - i * W;
+    int m = lane >> 2;
+    int ch = m * kHeadDim + (lane & 3) * 8;
+    const float* sp = samp + (size_t)warp * kSampW;
+    const float* Vr = V + (size_t)row * N * kE + ch;
+    float4 o01 = *reinterpret_cast<const float4*>(sp + m * 8);
+    float4 o23 = *reinterpret_cast<const float4*>(sp + m * 8 + 4);
+    float4 aw = *reinterpret_cast<const float4*>(sp + 64 + m * 4);
+    float offx[4] = {o01.x, o01.z, o23.x, o23.z};
+    float offy[4] = {o01.y, o01.w, o23.y, o23.w};
+    float a[4] = {aw.x, aw.y, aw.z, aw.w};
+    const float fW = (float)W, fH = (float)H;
+    const float refx = __fdiv_rn((float)j + 0.5f, fW);
+    const float refy = __fdiv_rn((float)i + 0.5f, fH);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int p = 0; p < kPoints; ++p) {
+        float lx = __fadd_rn(refx, __fdiv_rn(offx[p], fW));
+        float ly = __fadd_rn(refy, __fdiv_rn(offy[p], fH));
+        float gx = __fadd_rn(__fmul_rn(2.0f, lx), -1.0f);
+        float gy = __fadd_rn(__fmul_rn(2.0f, ly), -1.0f);
+        float x = __fadd_rn(__fmul_rn(__fadd_rn(gx, 1.0f), fW * 0.5f), -0.5f);
+        float y = __fadd_rn(__fmul_rn(__fadd_rn(gy, 1.0f), fH * 0.5f), -0.5f);
+        float xf = floorf(x), yf = floorf(y);
+        float wx1 = x - xf, wy1 = y - yf;
+        float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+        // guard against NaN/huge offsets before the int conversion
+        int x0 = (xf >= -2.0f && xf <= fW) ? (int)xf : -2;
+        int y0 = (yf >= -2.0f && yf <= fH) ? (int)yf : -2;
+        float s[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) s[c] = 0.f;
+#pragma unroll
+        for (int cy = 0; cy < 2; ++cy) {
+            int yy = y0 + cy;
+            if (yy < 0 || yy >= H) continue;
+            float wy = cy ? wy1 : wy0;
+#pragma unroll
+            for (int cx = 0; cx < 2; ++cx) {
+                int xx = x0 + cx;
+                if (xx < 0 || xx >= W) continue;
+                float wgt = wy * (cx ? wx1 : wx0);
+                const float* vp = Vr + (size_t)(yy * W + xx) * kE;
+                float4 v0 = __ldg(reinterpret_cast<const float4*>(vp));
+                float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + 4));
+                s[0] = fmaf(wgt, v0.x, s[0]); s[1] = fmaf(wgt, v0.y, s[1]);
+                s[2] = fmaf(wgt, v0.z, s[2]); s[3] = fmaf(wgt, v0.w, s[3]);
+                s[4] = fmaf(wgt, v1.x, s[4]); s[5] = fmaf(wgt, v1.y, s[5]);
+                s[6] = fmaf(wgt, v1.z, s[6]); s[7] = fmaf(wgt, v1.w, s[7]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(a[p], s[c], acc[c]);
+    }
+    float* op = out + (size_t)warp * kE + ch;
+    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// step epilogues
+// ------------------------------------------------------------------------------------------------
+// depth: q[row][n][c] = cond[b][n][c] + w_m[c] * d_t[row][n]      (down = ConvModule(257 -> 256), rank-1 half)
+__global__ void k_depth_head_in(const float* __restrict__ cond, const float* __restrict__ wm,
+                                const float* __restrict__ state, float* __restrict__ q, int N, int R,
+                                int total_tokens) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    size_t tok = idx / (kE / 4);
+    if (tok >= (size_t)total_tokens) return;
+    int c = (int)(idx % (kE / 4)) * 4;
+    int row = (int)(tok / N), n = (int)(tok % N);
+    int b = row / R;
+    float d = state[tok];
+    float4 cv = *reinterpret_cast<const float4*>(cond + ((size_t)b * N + n) * kE + c);
+    float4 wv = *reinterpret_cast<const float4*>(wm + c);
+    float4 o = make_float4(fmaf(wv.x, d, cv.x), fmaf(wv.y, d, cv.y), fmaf(wv.z, d, cv.z), fmaf(wv.w, d, cv.w));
+    *reinterpret_cast<float4*>(q + tok * kE + c) = o;
+}
+
+struct SegStepParams {
+    const float* logits;   // [rows][N][C]
+    float* state;          // [rows][N][256] in/out
+    float* accum;          // [B][N][C] running sum of softmax prob (accumulation) or of last-step logits
+    const float* lut;      // [(C+1)][256]
+    int N, R, C, B;
+    float alpha, sigma, alpha_next, sigma_next;
+    int accumulate_prob;   // accumulation=True: add softmax(logit) every step
+    int add_logits;        // accumulation=False and last step: add raw logits
+};
+
+// One warp per image token (b, n), looping over the R stochastic samples so that the accumulation
+// order is fixed.  ddp.py:235-243: argmax -> embedding -> squash -> DDIM update; softmax accumulate.
+__global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= p.B * p.N) return;
+    int b = warp / p.N, n = warp - b * p.N;
+    const int C = p.C;
+    const float sig = fmaxf(p.sigma, 1e-8f);
+    for (int r = 0; r < p.R; ++r) {
+        size_t tok = ((size_t)(b * p.R + r)) * p.N + n;
+        const float* lg = p.logits + tok * C;
+        float v[8];                      // C <= 256
+        float best = -INFINITY;
+        int besti = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int c = lane + k * 32;
+            v[k] = (c < C) ? lg[c] : -INFINITY;
+            if (c < C && (v[k] > best)) { best = v[k]; besti = c; }   // increasing c: first max wins
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (p.accumulate_prob) {
+            float e[8], s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int c = lane + k * 32;
+                e[k] = (c < C) ? expf(v[k] - best) : 0.f;
+                s += e[k];
+            }
+            s = warp_sum(s);
+            float* ac = p.accum + ((size_t)b * p.N + n) * C;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int c = lane + k * 32;
+                if (c < C) ac[c] += e[k] / s;
+            }
+        } else if (p.add_logits) {
+            float* ac = p.accum + ((size_t)b * p.N + n) * C;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int c = lane + k * 32;
+                if (c < C) ac[c] += v[k];
+            }
+        }
+        // m <- m_hat * alpha' + ((m - alpha * m_hat) / max(sigma, 1e-8)) * sigma'
+        const float* lr = p.lut + (size_t)besti * kE + lane * 8;
+        float* st = p.state + tok * kE + lane * 8;
+#pragma unroll
+        for (int h4 = 0; h4 < 2; ++h4) {
+            float4 mh = *reinterpret_cast<const float4*>(lr + h4 * 4);
+            float4 mt = *reinterpret_cast<const float4*>(st + h4 * 4);
+            float4 o;
+            o.x = __fadd_rn(__fmul_rn(mh.x, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.x, -__fmul_rn(p.alpha, mh.x)), sig), p.sigma_next));
+            o.y = __fadd_rn(__fmul_rn(mh.y, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.y, -__fmul_rn(p.alpha, mh.y)), sig), p.sigma_next));
+            o.z = __fadd_rn(__fmul_rn(mh.z, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.z, -__fmul_rn(p.alpha, mh.z)), sig), p.sigma_next));
+            o.w = __fadd_rn(__fmul_rn(mh.w, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.w, -__fmul_rn(p.alpha, mh.w)), sig), p.sigma_next));
+            *reinterpret_cast<float4*>(st + h4 * 4) = o;
+        }
+    }
+}
+
+// out[b][c][n] = accum[b][n][c] / count ; cls[b][n] = argmax_c out      (ddp.py:244-245 mean over dim 0)
+__global__ void k_seg_finalize(const float* __restrict__ accum, float* __restrict__ out, int32_t* __restrict__ cls,
+                               int N, int C, float count) {
+    __shared__ float tile[32][33];
+    int b = blockIdx.z;
+    int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* s = accum + (size_t)b * N * C;
+    float* d = out + (size_t)b * C * N;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int n = n0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (n < N && c < C) ? __fdiv_rn(s[(size_t)n * C + c], count) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, n = n0 + threadIdx.x;
+        if (n < N && c < C) d[(size_t)c * N + n] = tile[threadIdx.x][i];
+    }
+    if (cls != nullptr && blockIdx.y == 0) {
+        // one thread per token of this tile: argmax over all classes
+        int t = threadIdx.y * 32 + threadIdx.x;
+        if (t < 32) {
+            int n = n0 + t;
+            if (n < N) {
+                float best = -INFINITY; int bi = 0;
+                for (int c = 0; c < C; ++c) {
+                    float v = __fdiv_rn(s[(size_t)n * C + c], count);
+                    if (v > best) { best = v; bi = c; }
+                }
+                cls[(size_t)b * N + n] = bi;
+            }
+        }
+    }
+}
+
+struct DepthStepParams {
+    const float* taps;     // [rows][N][16]: per-token dot products with the 9 conv3x3 taps (cols 0..8)
+    float* state;          // [rows][N] depth_t in/out
+    float* pred;           // [rows][N] relu(conv)+min_depth (tap / last-step output), may be null
+    float* out;            // [B][N] final mean over r, clamped (written when last != 0)
+    int H, W, R, B;
+    float conv_bias, min_depth, max_depth, bit_scale;
+    float gamma_now, gamma_next;
+    int last;
+};
+
+// depth head tail + ddim_step.  depth/depth/models/decode_heads/decode_head.py:233-270 (relu(conv3x3)+min_depth),
+// depth/depth/models/depther/ddp.py:220-227, 240-246.  One thread per image token, looping over r.
+__global__ void k_depth_step(DepthStepParams p) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int N = p.H * p.W;
+    if (idx >= p.B * N) return;
+    int b = idx / N, n = idx - b * N;
+    int i = n / p.W, j = n - i * p.W;
+    float sum = 0.f;
+    const float sa_now = sqrtf(p.gamma_now), sa_next = sqrtf(p.gamma_next);
+    const float inv_sn = __fdiv_rn(1.0f, sqrtf(__fadd_rn(1.0f, -p.gamma_now)));
+    const float sn_next = sqrtf(__fadd_rn(1.0f, -p.gamma_next));
+    for (int r = 0; r < p.R; ++r) {
+        size_t base = ((size_t)(b * p.R + r)) * N;
+        float acc = 0.f;
+#pragma unroll
+        for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                int ii = i + di, jj = j + dj;
+                if (ii < 0 || ii >= p.H || jj < 0 || jj >= p.W) continue;
+                acc += p.taps[(base + (size_t)ii * p.W + jj) * 16 + (di + 1) * 3 + (dj + 1)];
+            }
+        float d = fmaxf(acc + p.conv_bias, 0.f) + p.min_depth;
+        if (p.pred) p.pred[base + n] = d;
+        sum += d;
+        float dn = __fdiv_rn(__fadd_rn(d, -p.min_depth), __fadd_rn(p.max_depth, -p.min_depth));
+        dn = __fmul_rn(__fadd_rn(__fmul_rn(dn, 2.0f), -1.0f), p.bit_scale);
+        dn = fminf(fmaxf(dn, -p.bit_scale), p.bit_scale);
+        float xt = p.state[base + n];
+        float eps = __fmul_rn(inv_sn, __fadd_rn(xt, -__fmul_rn(sa_now, dn)));
+        p.state[base + n] = __fadd_rn(__fmul_rn(sa_next, dn), __fmul_rn(sn_next, eps));
+    }
+    if (p.last) {
+        float o = __fdiv_rn(sum, (float)p.R);
+        p.out[idx] = fminf(fmaxf(o, p.min_depth), p.max_depth);
+    }
+}
+
+}  // namespace ddp

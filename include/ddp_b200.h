@@ -1,0 +1,175 @@
+/*
+ * ddp_b200.h — C ABI of the B200-native DDP reverse-diffusion decode head.
+ *
+ * One shared library (libddp_b200.so, sm_100a) owns the whole hot path of
+ * JiYuanFeng/DDP: the T-step "noise-to-map" sampling loop and the
+ * time-conditioned deformable-attention denoiser it calls.  The Python
+ * plug-in classes in ddp_b200/ (DDP, SelfAlignedDDP, DeformableHeadWithTime)
+ * bind these entry points with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - Every function returns 0 on success or a negative ddp_status; nothing
+ *     throws, nothing calls exit().  ddp_last_error() gives the message.
+ *   - x / noise / out / workspace are CALLER-OWNED DEVICE memory (e.g. a
+ *     torch tensor's data_ptr()); ddp_sample is asynchronous on `stream`
+ *     (a cudaStream_t passed as void*), the caller synchronises.
+ *   - After ddp_plan() the library neither allocates nor frees device memory.
+ *   - A handle is bound to the CUDA device current at ddp_create(); it is not
+ *     thread-safe, distinct handles are independent.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   ddp_create / ddp_set_weight   DDP.__init__                       segmentation/mmseg/models/segmentors/ddp.py:57-112
+ *                                 DeformableHeadWithTime.__init__    segmentation/mmseg/models/decode_heads/deformable_head_with_time.py:29-60
+ *                                 depth DDP.__init__                 depth/depth/models/depther/ddp.py:42-95
+ *   ddp_set_schedule              _get_sampling_timesteps, log_snr,  segmentation/mmseg/models/segmentors/ddp.py:14-28,204-213
+ *                                 gamma                              depth/depth/models/depther/ddp.py:207-218
+ *   ddp_sample                    DDP.ddim_sample                    segmentation/mmseg/models/segmentors/ddp.py:215-246
+ *                                 (calls DeformableHeadWithTime.forward deformable_head_with_time.py:90-132,
+ *                                  BaseTransformerLayer.forward      segmentation/mmseg/models/utils/transformer.py:374-419,
+ *                                  MultiScaleDeformableAttention.forward + ms_deform_attn_forward
+ *                                                                     mmcv/ops/multi_scale_deform_attn.py:252-358, 94-151)
+ *                                 depth DDP.sample + encode_decode clamp  depth/depth/models/depther/ddp.py:229-247, 97-110
+ */
+#ifndef DDP_B200_H_
+#define DDP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDP_ABI_VERSION 1
+
+typedef struct ddp_handle ddp_handle;
+
+typedef enum ddp_status {
+    DDP_OK = 0,
+    DDP_ERR_INVALID = -1,      /* bad argument / bad config (reference: ValueError, asserts)      */
+    DDP_ERR_UNSUPPORTED = -2,  /* valid in the reference, not built here (reference: NotImplementedError) */
+    DDP_ERR_STATE = -3,        /* call order: weights not committed, plan missing, ...            */
+    DDP_ERR_WORKSPACE = -4,    /* workspace too small or misaligned                               */
+    DDP_ERR_CUDA = -5,         /* a CUDA call failed; message holds cudaGetErrorString            */
+    DDP_ERR_WEIGHT = -6        /* unknown weight name or wrong element count                      */
+} ddp_status;
+
+enum { DDP_TASK_SEG = 0, DDP_TASK_DEPTH = 1 };
+enum { DDP_SCHEDULE_COSINE = 0, DDP_SCHEDULE_LINEAR = 1 };
+enum { DDP_DIFFUSION_DDIM = 0, DDP_DIFFUSION_DDPM = 1 };
+/* GEMM arithmetic.  FP32 = CUDA-core fp32 FMA.  TC_3XF16 = tcgen05 fp16 tensor cores with each fp32
+ * operand split into hi+lo halves and three MMAs per product (fp32-faithful, ~2^-22).  TC_F16 = one
+ * fp16 MMA per product (fast, NOT parity-grade; reported separately).                              */
+enum { DDP_GEMM_FP32 = 0, DDP_GEMM_TC_3XF16 = 1, DDP_GEMM_TC_F16 = 2 };
+
+typedef struct ddp_config {
+    int32_t abi_version;        /* DDP_ABI_VERSION */
+    int32_t task;               /* DDP_TASK_* */
+    int32_t num_classes;        /* seg: decode_head.num_classes (<= 256); depth: ignored */
+    int32_t timesteps;          /* DDP(timesteps=) */
+    int32_t time_difference;    /* DDP(time_difference=) */
+    int32_t noise_schedule;     /* DDP_SCHEDULE_* (seg only) */
+    int32_t diffusion;          /* DDP_DIFFUSION_* */
+    int32_t accumulation;       /* seg: DDP(accumulation=) */
+    int32_t learned_sinusoidal_dim; /* 16 */
+    int32_t num_layers;         /* encoder.num_layers, 6 in every shipped config (<= 8) */
+    int32_t gemm_mode;          /* DDP_GEMM_* */
+    float   sample_range_lo;    /* DDP(sample_range=)[0] */
+    float   bit_scale;          /* DDP(bit_scale=) */
+    float   min_depth;          /* depth */
+    float   max_depth;          /* depth */
+} ddp_config;
+
+/* Intermediate tensors that tests can copy out (ddp_add_tap) — token-major fp32,
+ * [rows][N][width] with rows = B*R, row = b*R + r, token n = i*w + j. */
+enum {
+    DDP_TAP_HEAD_IN = 0,   /* width 256: transform(cat[x, m_t]) tokens, layer ignored            */
+    DDP_TAP_VALUE = 1,     /* width 256: value_proj output of `layer`                            */
+    DDP_TAP_SAMPLING = 2,  /* width  96: 64 sampling offsets (head,point,xy) + 32 softmaxed weights */
+    DDP_TAP_GATHERED = 3,  /* width 256: ms_deform_attn output before output_proj                */
+    DDP_TAP_LN1 = 4,       /* width 256: after first LayerNorm                                   */
+    DDP_TAP_LAYER_OUT = 5, /* width 256: layer output (after FiLM)                               */
+    DDP_TAP_LOGITS = 6,    /* width C (seg) or 1 (depth: relu(conv)+min_depth), layer ignored    */
+    DDP_TAP_STATE = 7,     /* width Cin: m_t / depth_t AFTER the step's update, layer ignored    */
+    DDP_TAP_TEMB = 8,      /* [1024] time embedding of `step`                                    */
+    DDP_TAP_FILM = 9       /* [512] (scale | shift) of (`step`, `layer`)                         */
+};
+
+int ddp_abi_version(void);
+
+/* Create a handle on the current CUDA device.  Fails with DDP_ERR_CUDA when no sm_100 device is
+ * usable: there is no CPU fallback. */
+int ddp_create(const ddp_config* cfg, ddp_handle** out);
+void ddp_destroy(ddp_handle* h);
+const char* ddp_last_error(const ddp_handle* h);   /* h may be NULL: last create error */
+
+/* Weights, by the reference's state-dict key, as contiguous fp32 HOST arrays in the reference's
+ * own shapes (e.g. "transform.conv.weight" (256,512,1,1), "decode_head.encoder.layers.3.ffns.0.
+ * layers.0.0.weight" (1024,256); depth: "down.conv.weight" (256,257,1,1), "decode_head.conv_depth.
+ * weight" (1,256,3,3)).  Unknown names (backbone.*, neck.*, auxiliary_head.*) are rejected with
+ * DDP_ERR_WEIGHT so the caller can filter; ddp_weight_count/ddp_weight_name enumerate what is needed. */
+int ddp_weight_count(const ddp_handle* h);
+const char* ddp_weight_name(const ddp_handle* h, int index, int64_t* numel);
+int ddp_set_weight(ddp_handle* h, const char* name, const float* host_data, int64_t numel);
+/* Upload + repack into the kernels' layouts; fails if any weight is missing. */
+int ddp_commit_weights(ddp_handle* h);
+
+/* Optional: override the per-step schedule scalars computed by the library (plain C float math
+ * following ddp.py:14-28) with values the host computed, e.g. with the very torch ops the reference
+ * uses, so that they are bit-identical to a given reference run.  Arrays of length `timesteps`.
+ * seg:   time_in = log_snr(t_now) (input of time_mlp), a_now/s_now = alpha,sigma(t_now),
+ *        a_next/s_next = alpha,sigma(t_next).
+ * depth: time_in = t_now, a_now = gamma(t_now), a_next = gamma(t_next); s_* ignored. */
+int ddp_set_schedule(ddp_handle* h, int timesteps, const float* time_in, const float* a_now,
+                     const float* s_now, const float* a_next, const float* s_next);
+/* Read back the schedule in use (after ddp_plan). */
+int ddp_get_schedule(const ddp_handle* h, float* time_in, float* a_now, float* s_now,
+                     float* a_next, float* s_next);
+
+/* Fix the geometry: B images, R stochastic samples per image (randsteps), h x w tokens.  Builds the
+ * shape-only constants (sine positional encoding, its products with the offset/attention
+ * projections, time embeddings and FiLM vectors of all steps) and reports the workspace size. */
+int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspace_bytes);
+
+/* The sampling loop.
+ *   x      (B,256,h,w) fp32 NCHW   frozen conditioning feature (neck output)
+ *   noise  (B,R,Cin,h,w) fp32      initial state (ddp.py:220 draws it; here the caller does), Cin = 256 seg / 1 depth
+ *   out    (B,C,h,w) fp32          seg: mean logits, or mean softmax prob when accumulation; depth: (B,1,h,w) clamped
+ *   cls    (B,h,w) int32 or NULL   seg: argmax_C of `out`
+ * workspace: >= ddp_plan's size, 256-byte aligned. */
+int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies x and noise to the device, runs
+ * ddp_sample, copies out (and cls) back and synchronises the stream.  Uses the tail of the workspace
+ * for staging (ddp_plan's size already includes it). */
+int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host,
+                    int32_t* cls_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hooks.  A tap copies one intermediate of (step, layer) into caller-owned device memory during
+ * the next ddp_sample calls; ddp_set_state_override makes step `step` start from the given state
+ * ((B,R,Cin,h,w) device pointer, NCHW like `noise`) — teacher forcing.  ddp_clear_debug removes both. */
+int ddp_add_tap(ddp_handle* h, int kind, int step, int layer, float* device_dst);
+int ddp_set_state_override(ddp_handle* h, int step, const float* device_state);
+int ddp_clear_debug(ddp_handle* h);
+
+/* Number of kernel launches the last ddp_sample enqueued (for bench.py's gpu_launches). */
+int64_t ddp_last_launch_count(const ddp_handle* h);
+
+/* Per-kernel-class device timing: while enabled, every launch of ddp_sample is bracketed by CUDA
+ * events on the launching stream; ddp_profile_collect waits for them and returns, per class, the
+ * summed milliseconds and the number of launches since the last collect. */
+enum {
+    DDP_K_COND = 0, DDP_K_HEAD_IN, DDP_K_VALUE, DDP_K_SAMPLING, DDP_K_GATHER, DDP_K_OUT_PROJ,
+    DDP_K_FFN1, DDP_K_FFN2, DDP_K_HEAD_OUT, DDP_K_STEP, DDP_K_FINALIZE, DDP_K_LAYOUT, DDP_K_COUNT
+};
+int ddp_profile_enable(ddp_handle* h, int on);
+int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_class, int n_classes);
+const char* ddp_kernel_class_name(int cls);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDP_B200_H_ */

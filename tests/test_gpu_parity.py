@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against (1) the golden outputs of the
+unmodified reference and (2) the oracle, at sizes the oracle finishes in seconds, plus
+size-independent properties at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddp_oracle as O
+from golden_util import golden_files, load_case
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32"]
+
+
+def make_engine(cfg: O.OracleConfig, W, mode="fp32"):
+    from ddp_b200 import DecodeEngine
+    eng = DecodeEngine(task=cfg.task, num_classes=cfg.num_classes, timesteps=cfg.timesteps,
+                       time_difference=cfg.time_difference, sample_range=cfg.sample_range,
+                       noise_schedule=cfg.noise_schedule, accumulation=cfg.accumulation,
+                       bit_scale=cfg.bit_scale, num_layers=cfg.num_layers, min_depth=cfg.min_depth,
+                       max_depth=cfg.max_depth, gemm_mode=mode)
+    eng.load_state_dict(W)
+    return eng
+
+
+def argmax_report(a, b):
+    """-> (#mismatching pixels, #pixels)."""
+    am, bm = a.argmax(1), b.argmax(1)
+    return int((am != bm).sum()), am.numel()
+
+
+# tolerance on fp32 results computed in a different summation order (values are O(1))
+ATOL = 2e-4
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("path", golden_files("seg"), ids=lambda p: os.path.basename(p)[:-4])
+def test_seg_matches_reference_golden(path, mode):
+    cfg, W, x, noise, g = load_case(path)
+    eng = make_engine(cfg, W, mode)
+    eng.plan(1, cfg.randsteps, x.shape[2], x.shape[3])
+    taps = [eng.add_tap(6, k, -1, cfg.num_classes) for k in range(cfg.timesteps)]   # DDP_TAP_LOGITS
+    out, cls = eng.sample(x.cuda(), noise.cuda(), return_cls=True)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["out"])
+    out = out.cpu()
+    R, h, w, C = cfg.randsteps, x.shape[2], x.shape[3], cfg.num_classes
+    # per-step class maps (the index work of the loop): bit-exact against the reference
+    for k in range(cfg.timesteps):
+        lg = taps[k].cpu().view(R, h * w, C)
+        am = lg.argmax(2).view(R, h, w).numpy().astype(np.int16)
+        assert np.array_equal(am, g["step_argmax"][k]), f"step {k}: {(am != g['step_argmax'][k]).sum()} pixels differ"
+        ref_lg = torch.from_numpy(g["step_logits"][k]).permute(0, 2, 3, 1).reshape(R, h * w, C)
+        assert (lg - ref_lg).abs().max().item() < ATOL
+    assert (out - ref).abs().max().item() < ATOL
+    bad, tot = argmax_report(out, ref)
+    assert bad == 0, f"{bad}/{tot} final class-map pixels differ from the reference"
+    assert torch.equal(cls.cpu().long(), out.argmax(1))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("path", golden_files("depth"), ids=lambda p: os.path.basename(p)[:-4])
+def test_depth_matches_reference_golden(path, mode):
+    cfg, W, x, noise, g = load_case(path)
+    eng = make_engine(cfg, W, mode)
+    out = eng.sample(x.cuda(), noise.cuda()).cpu()
+    ref = torch.from_numpy(g["out"])
+    # north-star tolerance for depth: |delta| < 1e-3 (metres, after the clamp)
+    assert (out - ref).abs().max().item() < 1e-3
+    assert (out - ref).abs().max().item() < ATOL       # and in fact at fp32 rounding level
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_every_layer_against_oracle_teacher_forced(mode):
+    """Per-layer intermediates of every step, each step started from the ORACLE's state, so kernel
+    error is separated from the feedback cascade."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3, randsteps=2)
+    W = O.make_weights(cfg, seed=31)
+    B, h, w = 2, 10, 14
+    x, noise = O.make_inputs(cfg, B, h, w, seed=77)
+    ref, traces = O.sample(W, cfg, x, noise, trace=True)
+    eng = make_engine(cfg, W, mode)
+    eng.plan(B, cfg.randsteps, h, w)
+    R, N = cfg.randsteps, h * w
+    for k in range(1, cfg.timesteps):      # step k starts from the oracle's state after step k-1
+        st = torch.stack([traces[b].mask_t[k - 1] for b in range(B)])      # (B,R,256,h,w)
+        eng.set_state_override(k, st.cuda())
+    kinds = {"value": (1, 256), "sampling": (2, 96), "gathered": (3, 256), "ln1": (4, 256), "out": (5, 256)}
+    bufs = {}
+    for k in range(cfg.timesteps):
+        bufs[("head_in", k)] = eng.add_tap(0, k, -1, 256)
+        bufs[("logits", k)] = eng.add_tap(6, k, -1, cfg.num_classes)
+        bufs[("state", k)] = eng.add_tap(7, k, -1, 256)
+        for j in range(cfg.num_layers):
+            for name, (kind, width) in kinds.items():
+                bufs[(name, k, j)] = eng.add_tap(kind, k, j, width)
+    out = eng.sample(x.cuda(), noise.cuda()).cpu()
+    worst = {}
+
+    def cmp(key, got, want, tol):
+        d = (got - want).abs().max().item()
+        worst[key[0]] = max(worst.get(key[0], 0.0), d)
+        assert d < tol, f"{key}: max |d| = {d:.3e}"
+
+    def tok(t):    # (R,C,h,w) -> (R,N,C)
+        return t.flatten(2).transpose(1, 2)
+
+    for k in range(cfg.timesteps):
+        for b in range(B):
+            tr = traces[b]
+            sl = slice(b * R, (b + 1) * R)
+            cmp(("head_in", k), bufs[("head_in", k)].cpu().view(B * R, N, 256)[sl], tok(tr.feat[k]), 1e-4)
+            for j in range(cfg.num_layers):
+                t = tr.layers[k][j]
+                samp = torch.cat([t["offsets"], t["attn"]], dim=2)
+                cmp(("value", k, j), bufs[("value", k, j)].cpu().view(B * R, N, 256)[sl], t["value"], 1e-4)
+                cmp(("sampling", k, j), bufs[("sampling", k, j)].cpu().view(B * R, N, 96)[sl], samp, 1e-4)
+                cmp(("gathered", k, j), bufs[("gathered", k, j)].cpu().view(B * R, N, 256)[sl], t["gathered"], 1e-4)
+                cmp(("ln1", k, j), bufs[("ln1", k, j)].cpu().view(B * R, N, 256)[sl], t["ln1"], 1e-4)
+                cmp(("out", k, j), bufs[("out", k, j)].cpu().view(B * R, N, 256)[sl], t["out"], 2e-4)
+            lg = bufs[("logits", k)].cpu().view(B * R, N, cfg.num_classes)[sl]
+            cmp(("logits", k), lg, tok(tr.logits[k]), 2e-4)
+            assert torch.equal(lg.argmax(2), tok(tr.logits[k]).argmax(2)), f"step {k} argmax differs"
+            cmp(("state", k), bufs[("state", k)].cpu().view(B * R, N, 256)[sl], tok(tr.mask_t[k]), 1e-5)
+    assert (out - ref).abs().max().item() < ATOL
+    assert argmax_report(out, ref)[0] == 0
+    print("worst |d| per tensor:", {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", [
+    dict(task="seg", num_classes=150, T=3, R=1, acc=True, B=2, h=16, w=16),
+    dict(task="seg", num_classes=19, T=10, R=1, acc=False, B=2, h=8, w=24),
+    dict(task="seg", num_classes=19, T=2, R=8, acc=False, B=1, h=9, w=9),      # uncertainty mode, K=8 samples
+    dict(task="seg", num_classes=1, T=2, R=1, acc=False, B=1, h=5, w=6),       # single class
+    dict(task="seg", num_classes=256, T=1, R=1, acc=True, B=1, h=4, w=7),      # max classes
+    dict(task="seg", num_classes=19, T=1, R=1, acc=False, B=1, h=1, w=1),      # one token
+    dict(task="seg", num_classes=19, T=1, R=1, acc=False, B=1, h=1, w=67),     # one row, ragged
+    dict(task="depth", num_classes=1, T=20, R=1, acc=False, B=2, h=12, w=16),
+    dict(task="depth", num_classes=1, T=3, R=3, acc=False, B=2, h=7, w=5),
+], ids=lambda c: f"{c['task']}_C{c['num_classes']}_T{c['T']}_R{c['R']}_B{c['B']}_{c['h']}x{c['w']}")
+def test_against_oracle_end_to_end(case, mode):
+    cfg = O.OracleConfig(task=case["task"], num_classes=case["num_classes"], timesteps=case["T"],
+                         randsteps=case["R"], accumulation=case["acc"],
+                         bit_scale=0.01 if case["task"] == "seg" else 0.1)
+    W = O.make_weights(cfg, seed=40 + case["T"])
+    x, noise = O.make_inputs(cfg, case["B"], case["h"], case["w"], seed=500 + case["R"])
+    ref = O.sample(W, cfg, x, noise)
+    eng = make_engine(cfg, W, mode)
+    out = eng.sample(x.cuda(), noise.cuda()).cpu()
+    assert out.shape == ref.shape
+    d = (out - ref).abs().max().item()
+    if cfg.task == "seg":
+        assert d < ATOL, f"max |d| = {d:.3e}"
+        bad, tot = argmax_report(out, ref)
+        assert bad == 0, f"{bad}/{tot} class-map pixels differ"
+    else:
+        assert d < 1e-3 and d < ATOL, f"max |d| = {d:.3e}"
+
+
+def test_host_buffer_entry_point_equals_device_entry_point():
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    W = O.make_weights(cfg, seed=3)
+    x, noise = O.make_inputs(cfg, 2, 8, 8, seed=9)
+    eng = make_engine(cfg, W)
+    a = eng.sample(x.cuda(), noise.cuda()).cpu()
+    cls = torch.empty((2, 8, 8), dtype=torch.int32).pin_memory()
+    b = eng.sample_host(x.pin_memory(), noise.pin_memory(), cls=cls)
+    assert torch.equal(a, b)
+    assert torch.equal(cls.long(), a.argmax(1))
+
+
+def test_batched_call_equals_per_image_calls_bitwise():
+    """Images are independent: a batched call must equal per-image calls bit for bit,
+    and stochastic samples r only meet in the final mean."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3, randsteps=2)
+    W = O.make_weights(cfg, seed=8)
+    x, noise = O.make_inputs(cfg, 4, 24, 40, seed=10)
+    eng = make_engine(cfg, W)
+    full = eng.sample(x.cuda(), noise.cuda()).cpu()
+    for b in range(4):
+        one = eng.sample(x[b:b + 1].cuda(), noise[b:b + 1].cuda()).cpu()
+        assert torch.equal(full[b:b + 1], one)
+    # swapping the two samples of an image leaves the mean unchanged up to one rounding
+    sw = eng.sample(x.cuda(), noise.flip(1).cuda()).cpu()
+    assert (sw - full).abs().max().item() < 1e-6
+
+
+def test_full_size_properties_cityscapes_shape():
+    """BASELINE config 3 shape (128x256 tokens, 19 classes): size-independent properties.
+    accumulation output is a mean of softmaxes: rows sum to 1, values in [0,1]; determinism."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3, accumulation=True)
+    W = O.make_weights(cfg, seed=5)
+    x, noise = O.make_inputs(cfg, 2, 128, 256, seed=11)
+    eng = make_engine(cfg, W)
+    xc, nc = x.cuda(), noise.cuda()
+    out, cls = eng.sample(xc, nc, return_cls=True)
+    out2 = eng.sample(xc, nc)
+    assert torch.equal(out, out2), "kernels must be deterministic"
+    s = out.sum(1)
+    assert (s - 1).abs().max().item() < 1e-5
+    assert out.min().item() >= 0 and out.max().item() <= 1 + 1e-6
+    assert torch.equal(cls.long(), out.argmax(1))
+    # one image of the batch against the oracle would take ~1 min; a 1/16 crop of tokens cannot be
+    # compared (attention is spatial), so check one image of the batch equals its solo run instead
+    solo = eng.sample(xc[1:2], nc[1:2])
+    assert torch.equal(solo, out[1:2])
+
+
+def test_error_behaviour_mirrors_reference():
+    from ddp_b200 import DecodeEngine
+    from ddp_b200._lib import DDPError
+    with pytest.raises(ValueError, match="invalid noise schedule"):        # ddp.py:90
+        DecodeEngine(noise_schedule="quadratic")
+    with pytest.raises(NotImplementedError):                               # ddp.py:123
+        DecodeEngine(diffusion="euler")
+    eng = DecodeEngine(num_classes=19)
+    with pytest.raises(DDPError, match="ddp_commit_weights"):
+        eng.plan(1, 1, 4, 4)
+    with pytest.raises(KeyError):
+        eng.load_state_dict({})
+    cfg = O.OracleConfig(num_classes=19)
+    W = O.make_weights(cfg, seed=1)
+    bad = dict(W)
+    bad["decode_head.conv_seg.weight"] = torch.zeros(20, 256, 1, 1)
+    with pytest.raises(ValueError):
+        eng.load_state_dict(bad)
+    eng.load_state_dict({**W, "backbone.stem.weight": torch.zeros(3)})      # extra keys are ignored
+    with pytest.raises(DDPError):
+        DecodeEngine(num_classes=300)
+
+
+def test_library_schedule_close_to_reference_schedule():
+    """The C default schedule (plain float math) vs the host/torch one the plug-in hands over."""
+    from ddp_b200 import DecodeEngine
+    for T in (3, 10):
+        a = DecodeEngine(num_classes=19, timesteps=T, host_schedule=False).get_schedule()
+        b = DecodeEngine(num_classes=19, timesteps=T, host_schedule=True).get_schedule()
+        for col_a, col_b in zip(a, b):
+            assert np.allclose(col_a, col_b, rtol=2e-5, atol=2e-6), (col_a, col_b)
