@@ -15,6 +15,7 @@
 #include "../../include/ddp_b200.h"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
 
 using namespace ddp;
@@ -32,6 +33,15 @@ struct WeightSpec {
 struct LayerW {
     float *Wv_t, *bv, *Ws_t, *bs, *Wo_t, *bo, *W1_t, *b1, *W2_t, *b2, *g1, *e1, *g2, *e2, *Wt, *bt;
 };
+
+// one GEMM's weights for the tcgen05 path: fp16 planes [rows_pad][K] of 2^shift * W, their TMA maps
+struct TcWeight {
+    __half *hi = nullptr, *lo = nullptr;
+    CUtensorMap map_hi, map_lo;
+    float inv_scale = 1.f;      // 1 / (2^shift * activation scale): multiplies the accumulator
+    int rows_pad = 0, K = 0, bn = 0;
+};
+struct TcLayer { TcWeight v, s, o, f1, f2; };
 
 struct Tap { int kind, step, layer; float* dst; };
 struct ProfRec { int tag; cudaEvent_t a, b; };
@@ -54,6 +64,17 @@ struct ddp_handle {
     float conv_depth_bias = 0.f;
     float *t_w = nullptr, *t_W1 = nullptr, *t_b1 = nullptr, *t_W3 = nullptr, *t_b3 = nullptr;
     float *emb = nullptr, *lut = nullptr;
+
+    // tcgen05 path (gemm_mode != FP32)
+    bool tc = false;
+    int nsplit = 1;
+    int num_sms = 148;
+    __half* tc_arena = nullptr;
+    TcWeight tc_in, tc_out;
+    TcLayer tcL[kMaxLayers];
+    int out_bn = 32;
+    const void* maps_ws = nullptr;      // workspace the activation maps below were encoded for
+    CUtensorMap mA_state[2], mA_q[2], mA_g[2], mA_hid[2];
 
     // plan
     int B = 0, R = 0, H = 0, W = 0, N = 0, rows = 0;
@@ -260,6 +281,18 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
         LAUNCH_CHECK(h);                  \
     } while (0)
 
+// tcgen05 GEMM launch, dispatched on the split count of the handle
+#define TC_GEMM(h, tag, st, BN_, EPI_, aMaps, W, M_, ncols_pad, ep)                                                   \
+    do {                                                                                                              \
+        prof_begin(h, tag, st);                                                                                       \
+        cudaError_t e_ = (h)->nsplit == 3                                                                             \
+            ? tc::launch_gemm_tc<BN_, 3, EPI_>((aMaps)[0], (aMaps)[1], (W).map_hi, (W).map_lo, M_, (W).K, ncols_pad, ep, (h)->num_sms, st) \
+            : tc::launch_gemm_tc<BN_, 1, EPI_>((aMaps)[0], (aMaps)[0], (W).map_hi, (W).map_hi, M_, (W).K, ncols_pad, ep, (h)->num_sms, st); \
+        prof_end(h, st);                                                                                              \
+        if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "tcgen05 gemm setup failed: %s", cudaGetErrorString(e_));  \
+        LAUNCH_CHECK(h);                                                                                              \
+    } while (0)
+
 int repack(ddp_handle* h, const float* src, int rows, int K, int row_stride, int k_stride, int off,
            float* dst, int ld, int col0, cudaStream_t st) {
     int total = rows * K;
@@ -291,6 +324,87 @@ int compute_time_constants(ddp_handle* h, cudaStream_t st) {
     return DDP_OK;
 }
 
+
+// ---- tcgen05 path: weights as scaled fp16 planes + TMA maps ------------------------------------
+struct WPart { const float* dev; const std::vector<float>* host; int rows, row_stride, k_stride, off, row0; };
+
+int weight_shift(const std::vector<WPart>& parts) {
+    float mx = 0.f;
+    for (const WPart& p : parts)
+        for (float v : *p.host) mx = fmaxf(mx, fabsf(v));
+    if (!(mx > 0.f) || !isfinite(mx)) return 0;
+    int e;
+    frexpf(mx, &e);            // mx = f * 2^e, f in [0.5, 1)
+    return 8 - e;              // 2^shift * mx in [128, 256): hi and lo planes both normal fp16
+}
+
+int make_tc_weight(ddp_handle* h, TcWeight& tw, __half*& cursor, int rows_pad, int K, int bn,
+                   const std::vector<WPart>& parts, cudaStream_t st) {
+    tw.rows_pad = rows_pad; tw.K = K; tw.bn = bn;
+    tw.hi = cursor; cursor += (size_t)rows_pad * K;
+    tw.lo = cursor; cursor += (size_t)rows_pad * K;
+    const int shift = weight_shift(parts);
+    const float scale = ldexpf(1.0f, shift);
+    tw.inv_scale = 1.0f / (scale * tc::kActScale);
+    for (const WPart& p : parts) {
+        int total = p.rows * K;
+        k_split_weight<<<(total + 255) / 256, 256, 0, st>>>(p.dev, p.rows, K, p.row_stride, p.k_stride, p.off, scale,
+                                                            tw.hi, tw.lo, p.row0);
+        LAUNCH_CHECK(h);
+    }
+    if (!tc::make_map_f16(&tw.map_hi, tw.hi, rows_pad, K, bn) || !tc::make_map_f16(&tw.map_lo, tw.lo, rows_pad, K, bn))
+        return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight plane (%d x %d, box %d)", rows_pad, K, bn);
+    return DDP_OK;
+}
+
+int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
+    const ddp_config& c = h->cfg;
+    const int Lc = c.num_layers;
+    const bool seg = c.task == DDP_TASK_SEG;
+    const int Cout = seg ? c.num_classes : 9;
+    h->out_bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256));
+    size_t halves = 0;
+    auto need = [&](int rows_pad, int K) { halves += 2 * (size_t)rows_pad * K; };
+    need(kE, kE);
+    for (int j = 0; j < Lc; ++j) { need(kE, kE); need(128, kE); need(kE, kE); need(kFFN, kE); need(kE, kFFN); }
+    need(h->out_bn, kE);
+    if (h->tc_arena) { cudaFree(h->tc_arena); h->tc_arena = nullptr; }
+    CUDA_TRY(h, cudaMalloc(&h->tc_arena, halves * sizeof(__half)));
+    CUDA_TRY(h, cudaMemsetAsync(h->tc_arena, 0, halves * sizeof(__half), st));
+    __half* cur = h->tc_arena;
+    auto spec = [&](const std::string& n) { return find_spec(h, n); };
+    int rc;
+    if (seg) {
+        WeightSpec* w = spec("transform.conv.weight");        // (256, 512): the mask half is columns 256..511
+        if ((rc = make_tc_weight(h, h->tc_in, cur, kE, kE, 256, {{w->dev, &w->host, kE, 2 * kE, 1, kE, 0}}, st))) return rc;
+    }
+    for (int j = 0; j < Lc; ++j) {
+        std::string p = "decode_head.encoder.layers." + std::to_string(j) + ".";
+        TcLayer& T = h->tcL[j];
+        WeightSpec* wv = spec(p + "attentions.0.value_proj.weight");
+        WeightSpec* wo = spec(p + "attentions.0.sampling_offsets.weight");
+        WeightSpec* wa = spec(p + "attentions.0.attention_weights.weight");
+        WeightSpec* wp = spec(p + "attentions.0.output_proj.weight");
+        WeightSpec* w1 = spec(p + "ffns.0.layers.0.0.weight");
+        WeightSpec* w2 = spec(p + "ffns.0.layers.1.weight");
+        if ((rc = make_tc_weight(h, T.v, cur, kE, kE, 256, {{wv->dev, &wv->host, kE, kE, 1, 0, 0}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.s, cur, 128, kE, 128, {{wo->dev, &wo->host, 64, kE, 1, 0, 0},
+                                                             {wa->dev, &wa->host, 32, kE, 1, 0, 64}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.f1, cur, kFFN, kE, 256, {{w1->dev, &w1->host, kFFN, kE, 1, 0, 0}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st))) return rc;
+    }
+    if (seg) {
+        WeightSpec* w = spec("decode_head.conv_seg.weight");
+        if ((rc = make_tc_weight(h, h->tc_out, cur, h->out_bn, kE, h->out_bn, {{w->dev, &w->host, c.num_classes, kE, 1, 0, 0}}, st))) return rc;
+    } else {
+        WeightSpec* w = spec("decode_head.conv_depth.weight");   // (1, 256, 3, 3): row t = tap, element (t, c) at c*9 + t
+        if ((rc = make_tc_weight(h, h->tc_out, cur, h->out_bn, kE, h->out_bn, {{w->dev, &w->host, 9, 1, 9, 0, 0}}, st))) return rc;
+    }
+    return DDP_OK;
+}
+
+
 int do_tap(ddp_handle* h, int kind, int step, int layer, const float* src, size_t nfloats, cudaStream_t st) {
     for (const Tap& t : h->taps) {
         if (t.kind == kind && t.step == step && (t.layer == layer || layer < 0)) {
@@ -302,6 +416,7 @@ int do_tap(ddp_handle* h, int kind, int step, int layer, const float* src, size_
 
 struct Workspace {
     float *cond, *state, *q, *V, *samp, *g, *hid, *logits, *accum, *pred;
+    __half *state_hi, *state_lo, *q_hi, *q_lo, *g_hi, *g_lo, *hid_hi, *hid_lo;    // tcgen05 path: fp16 planes
     float *stage_x, *stage_noise, *stage_out;
     int32_t* stage_cls;
 };
@@ -313,13 +428,25 @@ size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_byt
     const size_t cout = c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 16;
     Bump b(base);
     Workspace w;
+    memset(&w, 0, sizeof(w));
+    auto half_planes = [&](size_t n, __half** hi, __half** lo) {       // two fp16 planes = n floats of space
+        *hi = reinterpret_cast<__half*>(b.take((n + 1) / 2));
+        *lo = reinterpret_cast<__half*>(b.take((n + 1) / 2));
+    };
     w.cond = b.take(B * N * kE);
     w.state = b.take(rows * N * cin);
     w.q = b.take(rows * N * kE);
     w.V = b.take(rows * N * kE);
     w.samp = b.take(rows * N * kSampW);
-    w.g = b.take(rows * N * kE);
-    w.hid = b.take(rows * N * kFFN);
+    w.g = b.take(rows * N * kE);        // tcgen05 path: only written when a GATHERED tap is registered
+    if (!h->tc) {
+        w.hid = b.take(rows * N * kFFN);
+    } else {
+        if (c.task == DDP_TASK_SEG) half_planes(rows * N * kE, &w.state_hi, &w.state_lo);
+        half_planes(rows * N * kE, &w.q_hi, &w.q_lo);
+        half_planes(rows * N * kE, &w.g_hi, &w.g_lo);
+        half_planes(rows * N * kFFN, &w.hid_hi, &w.hid_lo);
+    }
     w.logits = b.take(rows * N * cout);
     w.accum = b.take(B * N * (c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1));
     w.pred = b.take(rows * N);
@@ -330,6 +457,21 @@ size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_byt
     w.stage_cls = reinterpret_cast<int32_t*>(b.take(B * N));
     if (ws) *ws = w;
     return b.off;
+}
+
+int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& ws) {
+    if (h->maps_ws == ws_base) return DDP_OK;
+    const uint64_t M = (uint64_t)h->rows * h->N;
+    bool ok = true;
+    if (h->cfg.task == DDP_TASK_SEG) {
+        ok = ok && tc::make_map_f16(&h->mA_state[0], ws.state_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_state[1], ws.state_lo, M, kE, tc::BM);
+    }
+    ok = ok && tc::make_map_f16(&h->mA_q[0], ws.q_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_q[1], ws.q_lo, M, kE, tc::BM);
+    ok = ok && tc::make_map_f16(&h->mA_g[0], ws.g_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_g[1], ws.g_lo, M, kE, tc::BM);
+    ok = ok && tc::make_map_f16(&h->mA_hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&h->mA_hid[1], ws.hid_lo, M, kFFN, tc::BM);
+    if (!ok) return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation plane");
+    h->maps_ws = ws_base;
+    return DDP_OK;
 }
 
 }  // namespace
@@ -360,8 +502,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         return fail(nullptr, DDP_ERR_INVALID, "invalid noise schedule %d", cfg->noise_schedule);   // ddp.py:90 ValueError
     if (cfg->diffusion != DDP_DIFFUSION_DDIM)
         return fail(nullptr, DDP_ERR_UNSUPPORTED, "diffusion %d: only ddim is built", cfg->diffusion);   // ddp.py:123
-    if (cfg->gemm_mode != DDP_GEMM_FP32)
-        return fail(nullptr, DDP_ERR_UNSUPPORTED, "gemm_mode %d not built in this library", cfg->gemm_mode);
+    if (cfg->gemm_mode != DDP_GEMM_FP32 && cfg->gemm_mode != DDP_GEMM_TC_3XF16 && cfg->gemm_mode != DDP_GEMM_TC_F16)
+        return fail(nullptr, DDP_ERR_INVALID, "ddp_create: invalid gemm_mode %d", cfg->gemm_mode);
     if (cfg->task == DDP_TASK_DEPTH && !(cfg->max_depth > cfg->min_depth))
         return fail(nullptr, DDP_ERR_INVALID, "ddp_create: max_depth must exceed min_depth");
     int dev = 0;
@@ -377,6 +519,13 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
     ddp_handle* h = new ddp_handle();
     h->cfg = *cfg;
     h->device = dev;
+    h->tc = cfg->gemm_mode != DDP_GEMM_FP32;
+    h->nsplit = cfg->gemm_mode == DDP_GEMM_TC_3XF16 ? 3 : 1;
+    h->num_sms = prop.multiProcessorCount;
+    if (h->tc && !tc::get_encode_fn()) {
+        delete h;
+        return fail(nullptr, DDP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    }
     build_specs(h);
     default_schedule(h);
     *out = h;
@@ -390,6 +539,7 @@ void ddp_destroy(ddp_handle* h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& e : h->ev_pool) cudaEventDestroy(e);
     if (h->w_arena) cudaFree(h->w_arena);
+    if (h->tc_arena) cudaFree(h->tc_arena);
     if (h->p_arena) cudaFree(h->p_arena);
     delete h;
 }
@@ -493,6 +643,7 @@ int ddp_commit_weights(ddp_handle* h) {
     h->t_w = dev("time_mlp.0.weights");
     h->t_W1 = dev("time_mlp.1.weight"); h->t_b1 = dev("time_mlp.1.bias");
     h->t_W3 = dev("time_mlp.3.weight"); h->t_b3 = dev("time_mlp.3.bias");
+    if (h->tc && (rc = commit_tc_weights(h, st))) return rc;
     CUDA_TRY(h, cudaDeviceSynchronize());
     h->committed = true;
     h->planned = false;
@@ -561,6 +712,7 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     int rc = compute_time_constants(h, st);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->maps_ws = nullptr;
     h->ws_bytes = carve(h, nullptr, nullptr, &h->ws_compute_bytes);
     if (workspace_bytes) *workspace_bytes = h->ws_bytes;
     h->planned = true;
@@ -591,11 +743,17 @@ int ddp_clear_debug(ddp_handle* h) {
 
 int64_t ddp_last_launch_count(const ddp_handle* h) { return h ? h->launches : 0; }
 
-static int load_state(ddp_handle* h, const float* src_nchw, float* state, cudaStream_t st) {
+static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half* state_hi, __half* state_lo,
+                      cudaStream_t st) {
     const int N = h->N, rows = h->rows;
     if (h->cfg.task == DDP_TASK_SEG) {
         dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
         KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(src_nchw, state, kE, N)));
+        if (h->tc) {
+            size_t n8 = (size_t)rows * N * kE / 8;
+            KLAUNCH(h, DDP_K_LAYOUT, st, (k_split_planes<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
+                                              state, state_hi, h->nsplit == 3 ? state_lo : nullptr, n8)));
+        }
     } else {
         CUDA_TRY(h, cudaMemcpyAsync(state, src_nchw, (size_t)rows * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
@@ -628,20 +786,29 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
         EpiBias epi{ws.cond, h->b_tr, kE, kE, B * N};
         KLAUNCH(h, DDP_K_COND, st, (launch_gemm_simt<256, true>(x, 0, N, h->Wx_t, kE, B * N, kE, kE, epi, st)));
     }
-    if ((rc = load_state(h, noise, ws.state, st))) return rc;
+    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws))) return rc;
+    const bool s3 = h->nsplit == 3;
+    if ((rc = load_state(h, noise, ws.state, ws.state_hi, ws.state_lo, st))) return rc;
     if (seg) CUDA_TRY(h, cudaMemsetAsync(ws.accum, 0, (size_t)B * N * C * sizeof(float), st));
 
     for (int k = 0; k < T; ++k) {
         for (const Override& o : h->overrides)
-            if (o.step == k && (rc = load_state(h, o.src, ws.state, st))) return rc;
+            if (o.step == k && (rc = load_state(h, o.src, ws.state, ws.state_hi, ws.state_lo, st))) return rc;
         // head input tokens q = cond + W_m m_t
-        if (seg) {
+        if (seg && h->tc) {
+            tc::EpiParams ep{};
+            ep.scale = h->tc_in.inv_scale; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+            ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+            ep.cond = ws.cond; ep.N_tok = N; ep.R = R;
+            TC_GEMM(h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, h->mA_state, h->tc_in, M, kE, ep);
+        } else if (seg) {
             EpiAddCond epi{ws.q, ws.cond, N, R, M};
             KLAUNCH(h, DDP_K_HEAD_IN, st, (launch_gemm_simt<256, false>(ws.state, kE, 0, h->Wm_t, kE, M, kE, kE, epi, st)));
         } else {
-            size_t n4 = (size_t)M * (kE / 4);
+            size_t n8 = (size_t)M * (kE / 8);
             KLAUNCH(h, DDP_K_HEAD_IN, st,
-                    (k_depth_head_in<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(ws.cond, h->wm_vec, ws.state, ws.q, N, R, M)));
+                    (k_depth_head_in<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(ws.cond, h->wm_vec, ws.state, ws.q, ws.q_hi,
+                                                                                   s3 ? ws.q_lo : nullptr, N, R, M)));
         }
         if ((rc = do_tap(h, DDP_TAP_HEAD_IN, k, -1, ws.q, (size_t)M * kE, st))) return rc;
         if ((rc = do_tap(h, DDP_TAP_TEMB, k, -1, h->temb + (size_t)k * kTimeDim, kTimeDim, st))) return rc;
@@ -649,6 +816,48 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
         for (int j = 0; j < Lc; ++j) {
             const LayerW& L = h->L[j];
             const float* film = h->film + ((size_t)k * Lc + j) * 2 * kE;
+            if (h->tc) {
+                const TcLayer& T = h->tcL[j];
+                {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
+                    tc::EpiParams ep{};
+                    ep.scale = T.v.inv_scale; ep.bias = L.bv; ep.out = ws.V; ep.ldc = kE; ep.ncols = kE;
+                    TC_GEMM(h, DDP_K_VALUE, st, 256, tc::EPI_BIAS, h->mA_q, T.v, M, kE, ep);
+                }
+                {   // offsets / attention weights = proj(q + pos) = q W^T + pew
+                    tc::EpiParams ep{};
+                    ep.scale = T.s.inv_scale; ep.out = ws.samp; ep.ldc = kSampW; ep.ncols = kSampW; ep.pew = h->pew[j]; ep.N_tok = N;
+                    TC_GEMM(h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
+                }
+                if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
+                if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
+                bool want_g = false;
+                for (const Tap& t : h->taps) want_g = want_g || (t.kind == DDP_TAP_GATHERED && t.step == k && t.layer == j);
+                KLAUNCH(h, DDP_K_GATHER, st,
+                        (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
+                            ws.V, ws.samp, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, h->H, h->W, M)));
+                if (want_g && (rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
+                {   // q = LN1(q + output_proj(g))
+                    tc::EpiParams ep{};
+                    ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+                    ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                    ep.resid = ws.q; ep.gamma = L.g1; ep.beta = L.e1; ep.film = nullptr;
+                    TC_GEMM(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, T.o, M, kE, ep);
+                }
+                if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+                {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
+                    tc::EpiParams ep{};
+                    ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
+                    ep.split = tc::SplitOut{ws.hid_hi, ws.hid_lo, kFFN};
+                    TC_GEMM(h, DDP_K_FFN1, st, 256, tc::EPI_GELU, h->mA_q, T.f1, M, kFFN, ep);
+                }
+                {   // q = FiLM(LN2(q + hid W2^T + b2))
+                    tc::EpiParams ep{};
+                    ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+                    ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                    ep.resid = ws.q; ep.gamma = L.g2; ep.beta = L.e2; ep.film = film;
+                    TC_GEMM(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, T.f2, M, kE, ep);
+                }
+            } else {
             {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
                 EpiBias epi{ws.V, L.bv, kE, kE, M};
                 KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
@@ -660,7 +869,7 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
             if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
             if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
             KLAUNCH(h, DDP_K_GATHER, st,
-                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.samp, ws.g, h->H, h->W, M)));
+                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.samp, ws.g, nullptr, nullptr, h->H, h->W, M)));
             if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
             {   // q = LN1(q + output_proj(g))
                 EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
@@ -675,25 +884,43 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                 EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
                 KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
             }
+            }
             if ((rc = do_tap(h, DDP_TAP_LAYER_OUT, k, j, ws.q, (size_t)M * kE, st))) return rc;
             if ((rc = do_tap(h, DDP_TAP_FILM, k, j, film, 2 * kE, st))) return rc;
         }
 
         const bool last = (k == T - 1);
+        if (h->tc) {
+            tc::EpiParams ep{};
+            ep.scale = h->tc_out.inv_scale; ep.bias = seg ? h->b_out : nullptr; ep.out = ws.logits;
+            ep.ldc = seg ? C : 16; ep.ncols = seg ? C : 9;
+            switch (h->out_bn) {
+                case 32: TC_GEMM(h, DDP_K_HEAD_OUT, st, 32, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 32, ep); break;
+                case 64: TC_GEMM(h, DDP_K_HEAD_OUT, st, 64, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 64, ep); break;
+                case 128: TC_GEMM(h, DDP_K_HEAD_OUT, st, 128, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 128, ep); break;
+                default: TC_GEMM(h, DDP_K_HEAD_OUT, st, 256, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 256, ep); break;
+            }
+        }
         if (seg) {
-            EpiBias epi{ws.logits, h->b_out, C, C, M};
-            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 256, epi, st)));
+            if (!h->tc) {
+                EpiBias epi{ws.logits, h->b_out, C, C, M};
+                KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 256, epi, st)));
+            }
             if ((rc = do_tap(h, DDP_TAP_LOGITS, k, -1, ws.logits, (size_t)M * C, st))) return rc;
             SegStepParams p;
             p.logits = ws.logits; p.state = ws.state; p.accum = ws.accum; p.lut = h->lut;
+            p.state_hi = (h->tc && !last) ? ws.state_hi : nullptr;
+            p.state_lo = (h->tc && !last && s3) ? ws.state_lo : nullptr;
             p.N = N; p.R = R; p.C = C; p.B = B;
             p.alpha = h->a_now[k]; p.sigma = h->s_now[k]; p.alpha_next = h->a_next[k]; p.sigma_next = h->s_next[k];
             p.accumulate_prob = c.accumulation ? 1 : 0;
             p.add_logits = (!c.accumulation && last) ? 1 : 0;
             KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
         } else {
-            EpiBias epi{ws.logits, nullptr, 16, 9, M};
-            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 128, epi, st)));
+            if (!h->tc) {
+                EpiBias epi{ws.logits, nullptr, 16, 9, M};
+                KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 128, epi, st)));
+            }
             DepthStepParams p;
             p.taps = ws.logits; p.state = ws.state; p.pred = ws.pred; p.out = out;
             p.H = h->H; p.W = h->W; p.R = R; p.B = B;

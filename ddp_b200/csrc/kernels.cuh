@@ -1,9 +1,49 @@
 // Non-GEMM kernels of the DDP decode head: deformable gather, step epilogues (argmax -> embedding
 // LUT -> DDIM update, softmax accumulation), positional encoding, time embeddings, layout changes.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace ddp {
+
+// fp16 planes of an fp32 activation for the tensor-core GEMMs: hi = fp16(16 x), lo = fp16(16 x - hi)
+// (see gemm_tc.cuh); lo == nullptr stores the hi plane only.
+constexpr float kSplitScale = 16.0f;
+__device__ __forceinline__ void split8_store(const float (&v)[8], __half* hi, __half* lo) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float s = fminf(fmaxf(v[i] * kSplitScale, -65504.0f), 65504.0f);
+        h[i] = __float2half_rn(s);
+        l[i] = __float2half_rn(s - __half2float(h[i]));
+    }
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+// elementwise fp32 -> fp16 planes, n a multiple of 8
+__global__ void k_split_planes(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n8) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n8) return;
+    float4 a = *reinterpret_cast<const float4*>(src + idx * 8);
+    float4 b = *reinterpret_cast<const float4*>(src + idx * 8 + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    split8_store(v, hi + idx * 8, lo ? lo + idx * 8 : nullptr);
+}
+
+// weights: dst planes [rows_pad][K] fp16 of scale * src[r*row_stride + k*k_stride + off]; rows >= rows are zero
+__global__ void k_split_weight(const float* __restrict__ src, int rows, int K, int row_stride, int k_stride, int off,
+                               float scale, __half* __restrict__ hi, __half* __restrict__ lo, int row0) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * K) return;
+    int k = idx % K, r = idx / K;
+    float s = src[(size_t)r * row_stride + (size_t)k * k_stride + off] * scale;
+    __half hh = __float2half_rn(s);
+    hi[(size_t)(row0 + r) * K + k] = hh;
+    lo[(size_t)(row0 + r) * K + k] = __float2half_rn(s - __half2float(hh));
+}
 
 // ------------------------------------------------------------------------------------------------
 // layout changes
@@ -129,7 +169,7 @@ __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ l
 // zero padding outside the map.  One warp per token: lane = (head = lane / 4, 8 channels).
 __global__ void __launch_bounds__(256)
 k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float* __restrict__ out,
-              int H, int W, int total_tokens) {
+              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int total_tokens) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= total_tokens) return;
     int lane = threadIdx.x & 31;
@@ -191,9 +231,15 @@ k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = fmaf(a[p], s[c], acc[c]);
     }
-    float* op = out + (size_t)warp * kE + ch;
-    *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (out) {
+        float* op = out + (size_t)warp * kE + ch;
+        *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (out_hi) {
+        size_t o = (size_t)warp * kE + ch;
+        split8_store(acc, out_hi + o, out_lo ? out_lo + o : nullptr);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,24 +247,31 @@ k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float
 // ------------------------------------------------------------------------------------------------
 // depth: q[row][n][c] = cond[b][n][c] + w_m[c] * d_t[row][n]      (down = ConvModule(257 -> 256), rank-1 half)
 __global__ void k_depth_head_in(const float* __restrict__ cond, const float* __restrict__ wm,
-                                const float* __restrict__ state, float* __restrict__ q, int N, int R,
-                                int total_tokens) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
-    size_t tok = idx / (kE / 4);
+                                const float* __restrict__ state, float* __restrict__ q, __half* __restrict__ q_hi,
+                                __half* __restrict__ q_lo, int N, int R, int total_tokens) {
+    // two float4 per thread so that the fp16 planes can be stored 16 bytes at a time
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // 8-float index
+    size_t tok = idx / (kE / 8);
     if (tok >= (size_t)total_tokens) return;
-    int c = (int)(idx % (kE / 4)) * 4;
+    int c = (int)(idx % (kE / 8)) * 8;
     int row = (int)(tok / N), n = (int)(tok % N);
     int b = row / R;
     float d = state[tok];
-    float4 cv = *reinterpret_cast<const float4*>(cond + ((size_t)b * N + n) * kE + c);
-    float4 wv = *reinterpret_cast<const float4*>(wm + c);
-    float4 o = make_float4(fmaf(wv.x, d, cv.x), fmaf(wv.y, d, cv.y), fmaf(wv.z, d, cv.z), fmaf(wv.w, d, cv.w));
-    *reinterpret_cast<float4*>(q + tok * kE + c) = o;
+    const float* cp = cond + ((size_t)b * N + n) * kE + c;
+    float4 c0 = *reinterpret_cast<const float4*>(cp), c1 = *reinterpret_cast<const float4*>(cp + 4);
+    float4 w0 = *reinterpret_cast<const float4*>(wm + c), w1 = *reinterpret_cast<const float4*>(wm + c + 4);
+    float o[8] = {fmaf(w0.x, d, c0.x), fmaf(w0.y, d, c0.y), fmaf(w0.z, d, c0.z), fmaf(w0.w, d, c0.w),
+                  fmaf(w1.x, d, c1.x), fmaf(w1.y, d, c1.y), fmaf(w1.z, d, c1.z), fmaf(w1.w, d, c1.w)};
+    *reinterpret_cast<float4*>(q + tok * kE + c) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(q + tok * kE + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    if (q_hi) split8_store(o, q_hi + tok * kE + c, q_lo ? q_lo + tok * kE + c : nullptr);
 }
 
 struct SegStepParams {
     const float* logits;   // [rows][N][C]
     float* state;          // [rows][N][256] in/out
+    __half* state_hi;      // optional fp16 planes of the new state (A operand of the next head-in GEMM)
+    __half* state_lo;
     float* accum;          // [B][N][C] running sum of softmax prob (accumulation) or of last-step logits
     const float* lut;      // [(C+1)][256]
     int N, R, C, B;
@@ -280,6 +333,7 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
         // m <- m_hat * alpha' + ((m - alpha * m_hat) / max(sigma, 1e-8)) * sigma'
         const float* lr = p.lut + (size_t)besti * kE + lane * 8;
         float* st = p.state + tok * kE + lane * 8;
+        float nv[8];
 #pragma unroll
         for (int h4 = 0; h4 < 2; ++h4) {
             float4 mh = *reinterpret_cast<const float4*>(lr + h4 * 4);
@@ -290,6 +344,11 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
             o.z = __fadd_rn(__fmul_rn(mh.z, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.z, -__fmul_rn(p.alpha, mh.z)), sig), p.sigma_next));
             o.w = __fadd_rn(__fmul_rn(mh.w, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.w, -__fmul_rn(p.alpha, mh.w)), sig), p.sigma_next));
             *reinterpret_cast<float4*>(st + h4 * 4) = o;
+            nv[h4 * 4 + 0] = o.x; nv[h4 * 4 + 1] = o.y; nv[h4 * 4 + 2] = o.z; nv[h4 * 4 + 3] = o.w;
+        }
+        if (p.state_hi) {
+            size_t o8 = tok * kE + lane * 8;
+            split8_store(nv, p.state_hi + o8, p.state_lo ? p.state_lo + o8 : nullptr);
         }
     }
 }

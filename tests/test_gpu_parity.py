@@ -12,7 +12,7 @@ from golden_util import golden_files, load_case
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp32"]
+MODES = ["fp32", "tc_3xf16"]
 
 
 def make_engine(cfg: O.OracleConfig, W, mode="fp32"):
