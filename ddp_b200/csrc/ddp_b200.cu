@@ -81,6 +81,7 @@ struct ddp_handle {
     float* p_arena = nullptr;
     float *pe = nullptr, *pew[kMaxLayers] = {nullptr};
     float *d_time_in = nullptr, *four = nullptr, *h1 = nullptr, *temb = nullptr, *film = nullptr;
+    float *film_g = nullptr, *film_b = nullptr;     // LN2 gamma/beta with the FiLM (scale+1, shift) folded in, per (step, layer)
     size_t ws_bytes = 0, ws_compute_bytes = 0;
 
     // schedule (host)
@@ -282,16 +283,19 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
     } while (0)
 
 // tcgen05 GEMM launch, dispatched on the split count of the handle
-#define TC_GEMM(h, tag, st, BN_, EPI_, aMaps, W, M_, ncols_pad, ep)                                                   \
+#define TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep)                                      \
     do {                                                                                                              \
         prof_begin(h, tag, st);                                                                                       \
         cudaError_t e_ = (h)->nsplit == 3                                                                             \
-            ? tc::launch_gemm_tc<BN_, 3, EPI_>((aMaps)[0], (aMaps)[1], (W).map_hi, (W).map_lo, M_, (W).K, ncols_pad, ep, (h)->num_sms, st) \
-            : tc::launch_gemm_tc<BN_, 1, EPI_>((aMaps)[0], (aMaps)[0], (W).map_hi, (W).map_hi, M_, (W).K, ncols_pad, ep, (h)->num_sms, st); \
+            ? tc::launch_gemm_tc<BN_, 3, EPI_>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_hi, (W).map_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st) \
+            : tc::launch_gemm_tc<BN_, 1, EPI_>((aMaps)[0], (aMaps)[0], (a2Maps)[0], (a2Maps)[0], (W).map_hi, (W).map_hi, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st); \
         prof_end(h, st);                                                                                              \
         if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "tcgen05 gemm setup failed: %s", cudaGetErrorString(e_));  \
         LAUNCH_CHECK(h);                                                                                              \
     } while (0)
+
+#define TC_GEMM(h, tag, st, BN_, EPI_, aMaps, W, M_, ncols_pad, ep) \
+    TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, aMaps, (W).K, W, M_, ncols_pad, ep)
 
 int repack(ddp_handle* h, const float* src, int rows, int K, int row_stride, int k_stride, int off,
            float* dst, int ld, int col0, cudaStream_t st) {
@@ -319,6 +323,9 @@ int compute_time_constants(ddp_handle* h, cudaStream_t st) {
         k_gemv<1, 0><<<g2, 256, 0, st>>>(h->L[j].Wt, h->L[j].bt, h->temb, h->film + (size_t)j * 2 * kE,
                                          2 * kE, kTimeDim, kTimeDim, Lc * 2 * kE);
         LAUNCH_CHECK(h);
+        k_fold_film<<<(T * kE + 255) / 256, 256, 0, st>>>(h->film + (size_t)j * 2 * kE, Lc * 2 * kE, h->L[j].g2, h->L[j].e2,
+                                                         h->film_g + (size_t)j * kE, h->film_b + (size_t)j * kE, Lc * kE, T);
+        LAUNCH_CHECK(h);
     }
     h->time_dirty = false;
     return DDP_OK;
@@ -335,25 +342,32 @@ int weight_shift(const std::vector<WPart>& parts) {
     if (!(mx > 0.f) || !isfinite(mx)) return 0;
     int e;
     frexpf(mx, &e);            // mx = f * 2^e, f in [0.5, 1)
-    return 8 - e;              // 2^shift * mx in [128, 256): hi and lo planes both normal fp16
+    int s = 8 - e;             // 2^shift * mx in [128, 256): hi and lo planes both normal fp16
+    return s > 15 ? 15 : (s < -8 ? -8 : s);      // 2^shift itself must be an fp16 number (identity block)
 }
 
+// `residual` > 0 appends that many K columns holding 2^shift * I: [W | 2^shift I], so that A = [g | q] yields W g + q
 int make_tc_weight(ddp_handle* h, TcWeight& tw, __half*& cursor, int rows_pad, int K, int bn,
-                   const std::vector<WPart>& parts, cudaStream_t st) {
-    tw.rows_pad = rows_pad; tw.K = K; tw.bn = bn;
-    tw.hi = cursor; cursor += (size_t)rows_pad * K;
-    tw.lo = cursor; cursor += (size_t)rows_pad * K;
+                   const std::vector<WPart>& parts, cudaStream_t st, int residual = 0) {
+    const int Kt = K + residual;
+    tw.rows_pad = rows_pad; tw.K = Kt; tw.bn = bn;
+    tw.hi = cursor; cursor += (size_t)rows_pad * Kt;
+    tw.lo = cursor; cursor += (size_t)rows_pad * Kt;
     const int shift = weight_shift(parts);
     const float scale = ldexpf(1.0f, shift);
     tw.inv_scale = 1.0f / (scale * tc::kActScale);
     for (const WPart& p : parts) {
         int total = p.rows * K;
         k_split_weight<<<(total + 255) / 256, 256, 0, st>>>(p.dev, p.rows, K, p.row_stride, p.k_stride, p.off, scale,
-                                                            tw.hi, tw.lo, p.row0);
+                                                            tw.hi, tw.lo, p.row0, Kt);
         LAUNCH_CHECK(h);
     }
-    if (!tc::make_map_f16(&tw.map_hi, tw.hi, rows_pad, K, bn) || !tc::make_map_f16(&tw.map_lo, tw.lo, rows_pad, K, bn))
-        return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight plane (%d x %d, box %d)", rows_pad, K, bn);
+    if (residual) {
+        k_identity_block<<<(residual + 255) / 256, 256, 0, st>>>(tw.hi, residual, Kt, K, scale);
+        LAUNCH_CHECK(h);
+    }
+    if (!tc::make_map_f16(&tw.map_hi, tw.hi, rows_pad, Kt, bn) || !tc::make_map_f16(&tw.map_lo, tw.lo, rows_pad, Kt, bn))
+        return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight plane (%d x %d, box %d)", rows_pad, Kt, bn);
     return DDP_OK;
 }
 
@@ -366,7 +380,7 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
     size_t halves = 0;
     auto need = [&](int rows_pad, int K) { halves += 2 * (size_t)rows_pad * K; };
     need(kE, kE);
-    for (int j = 0; j < Lc; ++j) { need(kE, kE); need(128, kE); need(kE, kE); need(kFFN, kE); need(kE, kFFN); }
+    for (int j = 0; j < Lc; ++j) { need(kE, kE); need(128, kE); need(kE, 2 * kE); need(kFFN, kE); need(kE, kFFN + kE); }
     need(h->out_bn, kE);
     if (h->tc_arena) { cudaFree(h->tc_arena); h->tc_arena = nullptr; }
     CUDA_TRY(h, cudaMalloc(&h->tc_arena, halves * sizeof(__half)));
@@ -390,9 +404,9 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
         if ((rc = make_tc_weight(h, T.v, cur, kE, kE, 256, {{wv->dev, &wv->host, kE, kE, 1, 0, 0}}, st))) return rc;
         if ((rc = make_tc_weight(h, T.s, cur, 128, kE, 128, {{wo->dev, &wo->host, 64, kE, 1, 0, 0},
                                                              {wa->dev, &wa->host, 32, kE, 1, 0, 64}}, st))) return rc;
-        if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st, kE))) return rc;
         if ((rc = make_tc_weight(h, T.f1, cur, kFFN, kE, 256, {{w1->dev, &w1->host, kFFN, kE, 1, 0, 0}}, st))) return rc;
-        if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st))) return rc;
+        if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st, kE))) return rc;
     }
     if (seg) {
         WeightSpec* w = spec("decode_head.conv_seg.weight");
@@ -693,6 +707,7 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     need((size_t)N * kE);
     for (int j = 0; j < Lc; ++j) need((size_t)N * kSampW);
     need(T); need((size_t)T * 32); need((size_t)T * kTimeDim); need((size_t)T * kTimeDim); need((size_t)T * Lc * 2 * kE);
+    need((size_t)T * Lc * kE); need((size_t)T * Lc * kE);
     CUDA_TRY(h, cudaMalloc(&h->p_arena, fl * sizeof(float)));
     Bump b(h->p_arena);
     h->pe = b.take((size_t)N * kE);
@@ -700,6 +715,8 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     h->d_time_in = b.take(T); h->four = b.take((size_t)T * 32);
     h->h1 = b.take((size_t)T * kTimeDim); h->temb = b.take((size_t)T * kTimeDim);
     h->film = b.take((size_t)T * Lc * 2 * kE);
+    h->film_g = b.take((size_t)T * Lc * kE);
+    h->film_b = b.take((size_t)T * Lc * kE);
     cudaStream_t st = 0;
     k_sine_pe<<<(N * kE + 255) / 256, 256, 0, st>>>(h->pe, height, width);
     LAUNCH_CHECK(h);
@@ -840,8 +857,8 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                     tc::EpiParams ep{};
                     ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
                     ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                    ep.resid = ws.q; ep.gamma = L.g1; ep.beta = L.e1; ep.film = nullptr;
-                    TC_GEMM(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, T.o, M, kE, ep);
+                    ep.ln_g = L.g1; ep.ln_b = L.e1;
+                    TC_GEMM2(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
                 }
                 if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
                 {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
@@ -854,8 +871,8 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                     tc::EpiParams ep{};
                     ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
                     ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                    ep.resid = ws.q; ep.gamma = L.g2; ep.beta = L.e2; ep.film = film;
-                    TC_GEMM(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, T.f2, M, kE, ep);
+                    ep.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; ep.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
+                    TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
                 }
             } else {
             {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)

@@ -7,14 +7,15 @@
 // fp16 x fp16 products are exact in fp32, so the result is fp32-faithful (DDP_GEMM_TC_3XF16).
 // NSPLIT == 1 issues only the hi*hi MMA (DDP_GEMM_TC_F16, fast, not parity-grade).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A_hi, A_lo, W_hi, W_lo
 //            into a ring of shared-memory stages, completion on mbarriers.
 //   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) on
 //            shared-memory descriptors; tcgen05.commit releases stages / publishes accumulators.
-//   warps 2-5 epilogue: tcgen05.ld the 128 x BN fp32 accumulator from TMEM (thread = row), apply the
-//            fused epilogue, store.  Two accumulator buffers in TMEM let the epilogue of tile i
-//            overlap the MMAs of tile i+1.
+//   warps 2-9 epilogue: tcgen05.ld the 128 x BN fp32 accumulator from TMEM (thread = row, two warps per
+//            32-row lane quarter, each half of the columns), apply the fused epilogue, transpose through
+//            a per-warp shared-memory tile and store whole 128-byte lines.  Two accumulator buffers in
+//            TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -27,7 +28,6 @@ namespace tc {
 constexpr int BM = 128;        // rows per tile (UMMA M)
 constexpr int BK = 64;         // K elements per stage = one 128-byte swizzle atom of fp16
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
 constexpr float kActScale = 16.0f;       // activations are stored as fp16 planes of 16*x
 constexpr float kInvActScale = 1.0f / 16.0f;
 
@@ -100,38 +100,41 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// 32 lanes x 32 columns of fp32: thread t of the warp gets lane (lane_base + t), columns col..col+31
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+// 32 lanes x 64 columns of fp32: thread t of the warp gets lane (lane_base + t), columns col..col+63
+#define TMEM_R16(r, o) "=r"(r[o+0]), "=r"(r[o+1]), "=r"(r[o+2]), "=r"(r[o+3]), "=r"(r[o+4]), "=r"(r[o+5]), "=r"(r[o+6]), "=r"(r[o+7]), \
+                       "=r"(r[o+8]), "=r"(r[o+9]), "=r"(r[o+10]), "=r"(r[o+11]), "=r"(r[o+12]), "=r"(r[o+13]), "=r"(r[o+14]), "=r"(r[o+15])
+#define TMEM_W16(v, o) "r"(__float_as_uint(v[o+0])), "r"(__float_as_uint(v[o+1])), "r"(__float_as_uint(v[o+2])), "r"(__float_as_uint(v[o+3])), \
+                       "r"(__float_as_uint(v[o+4])), "r"(__float_as_uint(v[o+5])), "r"(__float_as_uint(v[o+6])), "r"(__float_as_uint(v[o+7])), \
+                       "r"(__float_as_uint(v[o+8])), "r"(__float_as_uint(v[o+9])), "r"(__float_as_uint(v[o+10])), "r"(__float_as_uint(v[o+11])), \
+                       "r"(__float_as_uint(v[o+12])), "r"(__float_as_uint(v[o+13])), "r"(__float_as_uint(v[o+14])), "r"(__float_as_uint(v[o+15]))
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : TMEM_R16(r, 0), TMEM_R16(r, 16)
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    tmem_ld32(taddr, &v[0]);
+    tmem_ld32(taddr + 32, &v[32]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
         "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr),
-          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        ::"r"(taddr), TMEM_W16(v, 0), TMEM_W16(v, 16)
         : "memory");
+}
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const float (&v)[64]) {
+    tmem_st32(taddr, &v[0]);
+    tmem_st32(taddr + 32, &v[32]);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
@@ -153,39 +156,80 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// fp32 -> (hi, lo) fp16 planes of kActScale * x
-__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
-    float s = fminf(fmaxf(x * kActScale, -65504.0f), 65504.0f);
-    hi = __float2half_rn(s);
-    lo = __float2half_rn(s - __half2float(hi));
-}
-
 // ---------------------------------------------------------------------------------------------
-// epilogues: thread owns one row (global row index `row`), columns arrive in chunks of 32
+// epilogue helpers.  A warp owns 32 rows (thread = row) and 64-column chunks; results go through a
+// 4 KB per-warp shared-memory tile so that global stores are whole 128-byte lines.
 // ---------------------------------------------------------------------------------------------
 struct SplitOut {            // optional fp16 planes of the output, row-major [M][ld]
     __half* hi; __half* lo; int ld;
 };
 
-__device__ __forceinline__ void store_row_f32(float* dst, const float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<float4*>(dst + i * 4) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+// gelu(x) = x * Phi(x), Phi via erf (Abramowitz-Stegun 7.1.26, |err(erf)| <= 1.5e-7), evaluated on |x| so that
+// the x < 0 branch has no cancellation.  nn.GELU() of the reference is the exact-erf form.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));          // MUFU.RCP, 1 ulp
+    float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    p *= t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * -1.44269504088896340736f));    // MUFU.EX2, 2 ulp
+    const float h = p * e;                                                                  // 0.5 * erfc(u)
+    return x * (x < 0.f ? h : 1.0f - h);
 }
-template <int NSPLIT>
-__device__ __forceinline__ void store_row_split(const SplitOut& o, size_t row, int col, const float (&v)[32]) {
-    __align__(16) __half h[32];
-    __align__(16) __half l[32];
+
+// 32 rows x 32 fp32 columns: thread `lane` holds its row's 32 values; writes rows [0, rows_valid) of the
+// warp's block to dst (row stride ld floats) as full 128-byte lines.
+__device__ __forceinline__ void stage_store_f32(float* stg, const float* v, float* dst, int ld, int rows_valid, int lane) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) split_f16(v[i], h[i], l[i]);
-    uint4* dh = reinterpret_cast<uint4*>(o.hi + row * o.ld + col);
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int c = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dh[i] = reinterpret_cast<const uint4*>(h)[i];
-    if (NSPLIT > 1) {
-        uint4* dl = reinterpret_cast<uint4*>(o.lo + row * o.ld + col);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dl[i] = reinterpret_cast<const uint4*>(l)[i];
+    for (int i = 0; i < 8; ++i) {
+        const int r = (lane >> 3) + 4 * i;
+        float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((c ^ (r & 7)) << 2));
+        if (r < rows_valid) *reinterpret_cast<float4*>(dst + (size_t)r * ld + c * 4) = x;
     }
+    __syncwarp();
+}
+// 32 rows x 64 fp16 columns (one plane): `h` = the row's 64 halves packed as 8 uint4
+__device__ __forceinline__ void stage_store_f16(float* stg, const uint4* h, __half* dst, int ld, int rows_valid, int lane) {
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s16[lane * 8 + (j ^ (lane & 7))] = h[j];
+    __syncwarp();
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = (lane >> 3) + 4 * i;
+        uint4 x = s16[r * 8 + (c ^ (r & 7))];
+        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c * 8) = x;
+    }
+    __syncwarp();
+}
+// fp16 planes of kActScale * v[0..63]; lo plane skipped when NSPLIT == 1
+template <int NSPLIT>
+__device__ __forceinline__ void split_store64(float* stg, const float (&v)[64], const SplitOut& o, size_t row0, int col,
+                                              int rows_valid, int lane) {
+    uint4 hi[8], lo[8];
+    __half2* h2 = reinterpret_cast<__half2*>(hi);
+    __half2* l2 = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float a = v[2 * i] * kActScale, b = v[2 * i + 1] * kActScale;
+        const __half2 hh = __floats2half2_rn(a, b);
+        h2[i] = hh;
+        if (NSPLIT > 1) {
+            const float2 back = __half22float2(hh);
+            l2[i] = __floats2half2_rn(a - back.x, b - back.y);
+        }
+    }
+    stage_store_f16(stg, hi, o.hi + row0 * o.ld + col, o.ld, rows_valid, lane);
+    if (NSPLIT > 1) stage_store_f16(stg, lo, o.lo + row0 * o.ld + col, o.ld, rows_valid, lane);
 }
 
 enum { EPI_BIAS = 0, EPI_ADD_COND = 1, EPI_SAMPLING = 2, EPI_GELU = 3, EPI_RES_LN = 4 };
@@ -201,34 +245,53 @@ struct EpiParams {
     const float* cond; int N_tok; int R;
     // EPI_SAMPLING
     const float* pew;
-    // EPI_RES_LN
-    const float* resid; const float* gamma; const float* beta; const float* film;
+    // EPI_RES_LN: y = LN(acc*scale + bias) * g + b; the residual is part of the accumulator (identity block of W),
+    // g / b already carry the FiLM (scale+1), shift
+    const float* ln_g; const float* ln_b;
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsTc = 32 * (2 + kEpiWarps);
+constexpr int kStageTileBytes = 4096;        // per-warp store staging tile
+
 template <int BN, int NSPLIT>
 struct Cfg {
     static constexpr int kABytes = BM * BK * 2;               // one fp16 plane of an A stage
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = NSPLIT == 1 ? (kABytes + kBBytes) : 2 * (kABytes + kBBytes);
-    static constexpr int kStages = (200 * 1024 / kStageBytes) > 6 ? 6 : (200 * 1024 / kStageBytes);
+    static constexpr int kStages = (192 * 1024 / kStageBytes) > 6 ? 6 : (192 * 1024 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiActive = BN >= 128 ? 8 : 4;      // epilogue warps that take part
+    static constexpr int kColsPerWarp = BN >= 128 ? BN / 2 : BN;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStageTileBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kStages >= 2, "need at least two stages");
-    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of sm_100");
 };
 
 template <int BN, int NSPLIT, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsTc, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapA2hi, const __grid_constant__ CUtensorMap mapA2lo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-               int M, int K, int n_tiles_n, EpiParams ep) {
+               int M, int K, int K1, int n_tiles_n, EpiParams ep) {
+    // A is the K-concatenation [A (K1 columns) | A2 (K - K1 columns)]: the residual of a post-norm block rides
+    // along as extra K against a scaled identity block of W, so the epilogue never reads it from global memory.
     using C = Cfg<BN, NSPLIT>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    // 1024-byte alignment (128B swizzle) by pointer arithmetic on the shared array, so that the compiler keeps
+    // the shared address space (LDS/STS instead of generic accesses) for the staging tiles
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* stage_tiles = smem + C::kStages * C::kStageBytes;
+    uint8_t* misc = stage_tiles + kEpiWarps * kStageTileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;     // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
@@ -239,14 +302,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     const int n_tiles_m = (M + BM - 1) / BM;
     const int n_tiles = n_tiles_m * n_tiles_n;
     const int n_kb = K / BK;
+    const int n_kb1 = K1 / BK;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
         if (NSPLIT > 1) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
+        if (n_kb1 < n_kb) { tma_prefetch_desc(&mapA2hi); if (NSPLIT > 1) tma_prefetch_desc(&mapA2lo); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], C::kEpiActive); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -267,10 +332,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * C::kStageBytes;
                     mbar_expect_tx(&full_bar[stage], C::kStageBytes);
-                    tma_load_2d(st, &mapAhi, &full_bar[stage], kb * BK, m0);
+                    const bool second = kb >= n_kb1;
+                    const int ka = (second ? kb - n_kb1 : kb) * BK;
+                    tma_load_2d(st, second ? &mapA2hi : &mapAhi, &full_bar[stage], ka, m0);
                     tma_load_2d(st + C::kABytes, &mapBhi, &full_bar[stage], kb * BK, n0);
                     if (NSPLIT > 1) {
-                        tma_load_2d(st + C::kABytes + C::kBBytes, &mapAlo, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(st + C::kABytes + C::kBBytes, second ? &mapA2lo : &mapAlo, &full_bar[stage], ka, m0);
                         tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &mapBlo, &full_bar[stage], kb * BK, n0);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -299,13 +366,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);       // +32 B per K=16 step inside the swizzle atom
-                        const uint32_t first = (kb | k) != 0;
+                        const uint32_t accum = (kb | k) != 0;
                         if (NSPLIT > 1) {
-                            umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, first);    // small terms first
+                            umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, accum);    // small terms first
                             umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
                             umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
                         } else {
-                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, first);
+                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, accum);
                         }
                     }
                     umma_commit(&empty_bar[stage]);                 // stage free once these MMAs retire
@@ -316,9 +383,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             }
         }
         __syncwarp();
-    } else {
-        // ===================== epilogue (warps 2..5): thread = row =====================
+    } else if (warp - 2 < C::kEpiActive) {
+        // ===================== epilogue: thread = row, 64-column chunks =====================
+        const int ew = warp - 2;
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                                // which half of the tile's columns
+        const int cbeg = half * C::kColsPerWarp;
+        float* stg = reinterpret_cast<float*>(stage_tiles + ew * kStageTileBytes);
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles_n) * BM;
@@ -326,106 +397,140 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
-            const size_t srow = row_ok ? (size_t)row : (size_t)(M - 1);
+            const int wrow0 = m0 + q * 32;                       // first row of this warp's 32-row block
+            const int row = wrow0 + lane;
+            const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
+            const size_t srow = row < M ? (size_t)row : (size_t)(M - 1);
 
             if (EPI == EPI_RES_LN) {
-                // pass 1: x = acc*scale + bias + resid -> back into TMEM; robust mean / M2 (Chan merge of 32-chunks)
+                // pass 1: x = acc*scale + bias (residual included via the identity block) -> back into TMEM;
+                // robust mean / M2 (Chan merge of 64-chunks)
                 float mean = 0.f, m2 = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    float v[32];
-                    tmem_ld32(t_row + c, v);
-                    const float* rp = ep.resid + srow * kE + c;
+                for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {
+                    float v[64];
+                    tmem_ld64(t_row + c, v);
                     float cs = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 r4 = *reinterpret_cast<const float4*>(rp + i * 4);
-                        float4 b4 = *reinterpret_cast<const float4*>(ep.bias + c + i * 4);
-                        v[i * 4 + 0] = (v[i * 4 + 0] * ep.scale + b4.x) + r4.x;
-                        v[i * 4 + 1] = (v[i * 4 + 1] * ep.scale + b4.y) + r4.y;
-                        v[i * 4 + 2] = (v[i * 4 + 2] * ep.scale + b4.z) + r4.z;
-                        v[i * 4 + 3] = (v[i * 4 + 3] * ep.scale + b4.w) + r4.w;
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + i * 4));
+                        v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, b4.x);      // the accumulator already holds W g + residual
+                        v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, b4.y);
+                        v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, b4.z);
+                        v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, b4.w);
                         cs += (v[i * 4 + 0] + v[i * 4 + 1]) + (v[i * 4 + 2] + v[i * 4 + 3]);
                     }
-                    tmem_st32(t_row + c, v);
-                    const float cm = cs * (1.0f / 32.0f);
+                    tmem_st64(t_row + c, v);
+                    const float cm = cs * (1.0f / 64.0f);
                     float cm2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) { float d = v[i] - cm; cm2 = fmaf(d, d, cm2); }
-                    const float na = (float)c, nb = 32.0f, nab = na + nb;
+                    for (int i = 0; i < 64; ++i) { const float d = v[i] - cm; cm2 = fmaf(d, d, cm2); }
+                    const float na = (float)(c - cbeg), nb = 64.0f, nab = na + nb;
                     const float delta = cm - mean;
                     mean += delta * (nb / nab);
                     m2 += cm2 + delta * delta * (na * nb / nab);
                 }
-                const float rstd = 1.0f / sqrtf(m2 * (1.0f / BN) + 1e-5f);
-                // pass 2: normalise, FiLM, store
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    float v[32];
-                    tmem_ld32(t_row + c, v);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float y = (v[i] - mean) * rstd * ep.gamma[c + i] + ep.beta[c + i];
-                        if (ep.film) y = y * (ep.film[c + i] + 1.0f) + ep.film[kE + c + i];
-                        v[i] = y;
-                    }
-                    if (row_ok) {
-                        store_row_f32(ep.out + (size_t)row * ep.ldc + c, v);
-                        if (ep.split.hi) store_row_split<NSPLIT>(ep.split, (size_t)row, c, v);
-                    }
+                // combine with the warp that owns the other half of the columns of the same rows: each warp
+                // drops its partial into the PARTNER's staging tile (idle between the two passes) and reads its own
+                {
+                    float2* mine = reinterpret_cast<float2*>(stg);
+                    float2* theirs = reinterpret_cast<float2*>(stage_tiles + (ew ^ 4) * kStageTileBytes);
+                    theirs[lane] = make_float2(mean, m2);
+                    named_bar_sync(1 + q, 64);
+                    const float2 o = mine[lane];
+                    const float2 lo_half = half == 0 ? make_float2(mean, m2) : o;     // same operand order in both warps
+                    const float2 hi_half = half == 0 ? o : make_float2(mean, m2);
+                    const float delta = hi_half.x - lo_half.x;
+                    mean = lo_half.x + delta * 0.5f;
+                    m2 = (lo_half.y + hi_half.y) + delta * delta * ((float)(C::kColsPerWarp) * 0.5f);
+                    __syncwarp();
                 }
+                const float rstd = 1.0f / sqrtf(m2 * (1.0f / BN) + 1e-5f);
+                // pass 2: normalise (+FiLM, folded into ln_g / ln_b), store
+#pragma unroll 1
+                for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {
+                    float v[64];
+                    tmem_ld64(t_row + c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_g + c + i * 4));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.ln_b + c + i * 4));
+                        v[i * 4 + 0] = fmaf((v[i * 4 + 0] - mean) * rstd, g4.x, b4.x);
+                        v[i * 4 + 1] = fmaf((v[i * 4 + 1] - mean) * rstd, g4.y, b4.y);
+                        v[i * 4 + 2] = fmaf((v[i * 4 + 2] - mean) * rstd, g4.z, b4.z);
+                        v[i * 4 + 3] = fmaf((v[i * 4 + 3] - mean) * rstd, g4.w, b4.w);
+                    }
+                    float* dst = ep.out + (size_t)wrow0 * ep.ldc + c;
+                    stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
+                    stage_store_f32(stg, &v[32], dst + 32, ep.ldc, rows_valid, lane);
+                    if (ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, c, rows_valid, lane);
+                }
+                named_bar_sync(1 + q, 64);        // the partner may write the next tile's partials into this tile only now
             } else {
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    float v[32];
-                    tmem_ld32(t_row + c, v);
+                for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {
+                    constexpr int W = C::kColsPerWarp < 64 ? C::kColsPerWarp : 64;     // 32 or 64 columns this round
+                    float v[64];
+                    tmem_ld32(t_row + c, &v[0]);
+                    if (W == 64) tmem_ld32(t_row + c + 32, &v[32]);
                     const int col0 = n0 + c;
                     if (EPI == EPI_ADD_COND) {
                         const int n = (int)(srow % ep.N_tok);
                         const int b = (int)(srow / ep.N_tok) / ep.R;
                         const float* cp = ep.cond + ((size_t)b * ep.N_tok + n) * kE + col0;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float4 c4 = *reinterpret_cast<const float4*>(cp + i * 4);
-                            v[i * 4 + 0] = v[i * 4 + 0] * ep.scale + c4.x; v[i * 4 + 1] = v[i * 4 + 1] * ep.scale + c4.y;
-                            v[i * 4 + 2] = v[i * 4 + 2] * ep.scale + c4.z; v[i * 4 + 3] = v[i * 4 + 3] * ep.scale + c4.w;
+                        for (int i = 0; i < W / 4; ++i) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(cp + i * 4);
+                            v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, c4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, c4.y);
+                            v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, c4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, c4.w);
                         }
                     } else if (EPI == EPI_SAMPLING) {
+                        // columns 0..63 offsets (half 0), 64..95 attention logits, 96..127 padding (half 1)
                         const int n = (int)(srow % ep.N_tok);
                         const float* pp = ep.pew + (size_t)n * kSampW + col0;
+                        const int nvalid = col0 < 64 ? 64 : 32;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = (col0 + i < kSampW) ? v[i] * ep.scale + pp[i] : 0.f;
+                        for (int i = 0; i < W / 4; ++i) {
+                            if (i * 4 < nvalid) {
+                                const float4 p4 = *reinterpret_cast<const float4*>(pp + i * 4);
+                                v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, p4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, p4.y);
+                                v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, p4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, p4.w);
+                            }
+                        }
                         if (col0 >= 64) {           // attention weights: softmax over each head's 4 points
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
-                                float mx = fmaxf(fmaxf(v[g * 4], v[g * 4 + 1]), fmaxf(v[g * 4 + 2], v[g * 4 + 3]));
-                                float e0 = expf(v[g * 4] - mx), e1 = expf(v[g * 4 + 1] - mx), e2 = expf(v[g * 4 + 2] - mx), e3 = expf(v[g * 4 + 3] - mx);
-                                float s = (e0 + e1) + (e2 + e3);
-                                v[g * 4] = e0 / s; v[g * 4 + 1] = e1 / s; v[g * 4 + 2] = e2 / s; v[g * 4 + 3] = e3 / s;
+                                const float mx = fmaxf(fmaxf(v[g * 4], v[g * 4 + 1]), fmaxf(v[g * 4 + 2], v[g * 4 + 3]));
+                                const float e0 = expf(v[g * 4] - mx), e1 = expf(v[g * 4 + 1] - mx), e2 = expf(v[g * 4 + 2] - mx), e3 = expf(v[g * 4 + 3] - mx);
+                                const float sden = (e0 + e1) + (e2 + e3);
+                                v[g * 4] = e0 / sden; v[g * 4 + 1] = e1 / sden; v[g * 4 + 2] = e2 / sden; v[g * 4 + 3] = e3 / sden;
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float x = v[i] * ep.scale + (ep.bias ? ep.bias[col0 + i] : 0.f);
-                            if (EPI == EPI_GELU) x = gelu_erf(x);
-                            v[i] = x;
-                        }
-                    }
-                    if (row_ok) {
-                        if (ep.out) {
-                            if (col0 + 32 <= ep.ncols && (ep.ldc & 3) == 0) {
-                                store_row_f32(ep.out + (size_t)row * ep.ldc + col0, v);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    if (col0 + i < ep.ncols) ep.out[(size_t)row * ep.ldc + col0 + i] = v[i];
+                        for (int i = 0; i < W / 4; ++i) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ep.bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i * 4));
+                            v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, b4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, b4.y);
+                            v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, b4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, b4.w);
+                            if (EPI == EPI_GELU) {
+                                v[i * 4 + 0] = gelu_fast(v[i * 4 + 0]); v[i * 4 + 1] = gelu_fast(v[i * 4 + 1]);
+                                v[i * 4 + 2] = gelu_fast(v[i * 4 + 2]); v[i * 4 + 3] = gelu_fast(v[i * 4 + 3]);
                             }
                         }
-                        if (ep.split.hi) store_row_split<NSPLIT>(ep.split, (size_t)row, col0, v);
                     }
+                    if (ep.out) {
+                        if ((ep.ldc & 3) == 0 && col0 + 32 <= ep.ncols) {
+                            float* dst = ep.out + (size_t)wrow0 * ep.ldc + col0;
+                            stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
+                            if (W == 64 && col0 + 64 <= ep.ncols) stage_store_f32(stg, &v[32], dst + 32, ep.ldc, rows_valid, lane);
+                        } else if (row < M) {
+#pragma unroll
+                            for (int i = 0; i < W; ++i)
+                                if (col0 + i < ep.ncols) ep.out[(size_t)row * ep.ldc + col0 + i] = v[i];
+                        }
+                    }
+                    if (W == 64 && ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, col0, rows_valid, lane);
                 }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -476,9 +581,9 @@ inline bool make_map_f16(CUtensorMap* map, const void* base, uint64_t rows, uint
 }
 
 template <int BN, int NSPLIT, int EPI>
-inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& bHi,
-                                  const CUtensorMap& bLo, int M, int K, int n_cols_padded, const EpiParams& ep,
-                                  int num_sms, cudaStream_t st) {
+inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& a2Hi,
+                                  const CUtensorMap& a2Lo, const CUtensorMap& bHi, const CUtensorMap& bLo, int M, int K,
+                                  int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st) {
     using C = Cfg<BN, NSPLIT>;
     static bool attr_set = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, EPI>;
@@ -490,7 +595,7 @@ inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo
     const int n_tiles_n = n_cols_padded / BN;
     const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    kern<<<grid, kThreads, C::kSmemBytes, st>>>(aHi, aLo, bHi, bLo, M, K, n_tiles_n, ep);
+    kern<<<grid, kThreadsTc, C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
     return cudaSuccess;
 }
 

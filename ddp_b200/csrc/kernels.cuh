@@ -35,14 +35,19 @@ __global__ void k_split_planes(const float* __restrict__ src, __half* __restrict
 
 // weights: dst planes [rows_pad][K] fp16 of scale * src[r*row_stride + k*k_stride + off]; rows >= rows are zero
 __global__ void k_split_weight(const float* __restrict__ src, int rows, int K, int row_stride, int k_stride, int off,
-                               float scale, __half* __restrict__ hi, __half* __restrict__ lo, int row0) {
+                               float scale, __half* __restrict__ hi, __half* __restrict__ lo, int row0, int ld) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * K) return;
     int k = idx % K, r = idx / K;
     float s = src[(size_t)r * row_stride + (size_t)k * k_stride + off] * scale;
     __half hh = __float2half_rn(s);
-    hi[(size_t)(row0 + r) * K + k] = hh;
-    lo[(size_t)(row0 + r) * K + k] = __float2half_rn(s - __half2float(hh));
+    hi[(size_t)(row0 + r) * ld + k] = hh;
+    lo[(size_t)(row0 + r) * ld + k] = __float2half_rn(s - __half2float(hh));
+}
+// scaled identity block: hi[r][col0 + r] = c (a power of two), used to carry a residual through the GEMM
+__global__ void k_identity_block(__half* __restrict__ hi, int n, int ld, int col0, float c) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) hi[(size_t)r * ld + col0 + r] = __float2half_rn(c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -149,6 +154,19 @@ __global__ void k_gemv(const float* __restrict__ Wm, const float* __restrict__ b
     }
 }
 
+// LN2 followed by FiLM, y = (n * gamma + beta) * (scale + 1) + shift, as one affine map of the normalised value n:
+// g = gamma * (scale + 1), b = beta * (scale + 1) + shift   (transformer.py:390-392 then 413-417)
+__global__ void k_fold_film(const float* __restrict__ film, int film_stride, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float* __restrict__ g, float* __restrict__ b, int out_stride, int T) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * kE) return;
+    int t = idx / kE, c = idx % kE;
+    float sc = film[(size_t)t * film_stride + c] + 1.0f;
+    float sh = film[(size_t)t * film_stride + kE + c];
+    g[(size_t)t * out_stride + c] = gamma[c] * sc;
+    b[(size_t)t * out_stride + c] = fmaf(beta[c], sc, sh);
+}
+
 // (sigmoid(E[c]) * 2 - 1) * bit_scale    segmentation/mmseg/models/segmentors/ddp.py:236-237
 __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ lut, int n, float bit_scale) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,7 +184,41 @@ __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ l
 //   loc = ref + off / W                 vmmcv/ops/multi_scale_deform_attn.py:329-334
 //   grid = 2 loc - 1                    :121
 //   x = (grid + 1) * (W / 2) - .5       F.grid_sample(align_corners=False) unnormalisation
-// zero padding outside the map.  One warp per token: lane = (head = lane / 4, 8 channels).
+// zero padding outside the map.  One warp per token.  Lane = (head-in-group = lane / 8, 4 channels); the warp walks
+// two groups of 4 heads, so every warp-wide float4 load covers four whole 128-byte lines (one per head): the minimum
+// number of L1 wavefronts for this access pattern (16 KB of V per token).
+__device__ __forceinline__ void msda_point(const float* __restrict__ Vr, float offx, float offy, float a, float refx, float refy,
+                                           float fW, float fH, int W, int H, float (&acc)[4]) {
+    float lx = __fadd_rn(refx, __fdiv_rn(offx, fW));
+    float ly = __fadd_rn(refy, __fdiv_rn(offy, fH));
+    float gx = __fadd_rn(__fmul_rn(2.0f, lx), -1.0f);
+    float gy = __fadd_rn(__fmul_rn(2.0f, ly), -1.0f);
+    float x = __fadd_rn(__fmul_rn(__fadd_rn(gx, 1.0f), fW * 0.5f), -0.5f);
+    float y = __fadd_rn(__fmul_rn(__fadd_rn(gy, 1.0f), fH * 0.5f), -0.5f);
+    float xf = floorf(x), yf = floorf(y);
+    float wx1 = x - xf, wy1 = y - yf;
+    float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    // guard against NaN / huge offsets before the int conversion
+    int x0 = (xf >= -2.0f && xf <= fW) ? (int)xf : -2;
+    int y0 = (yf >= -2.0f && yf <= fH) ? (int)yf : -2;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy) {
+        int yy = y0 + cy;
+        if (yy < 0 || yy >= H) continue;
+        float wy = cy ? wy1 : wy0;
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+            int xx = x0 + cx;
+            if (xx < 0 || xx >= W) continue;
+            float wgt = wy * (cx ? wx1 : wx0);
+            float4 v = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(yy * W + xx) * kE));
+            s0 = fmaf(wgt, v.x, s0); s1 = fmaf(wgt, v.y, s1); s2 = fmaf(wgt, v.z, s2); s3 = fmaf(wgt, v.w, s3);
+        }
+    }
+    acc[0] = fmaf(a, s0, acc[0]); acc[1] = fmaf(a, s1, acc[1]); acc[2] = fmaf(a, s2, acc[2]); acc[3] = fmaf(a, s3, acc[3]);
+}
+
 __global__ void __launch_bounds__(256)
 k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float* __restrict__ out,
               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int total_tokens) {
@@ -176,69 +228,36 @@ k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float
     int N = H * W;
     int row = warp / N, n = warp - row * N;
     int i = n / W, j = n - i * W;
-    int m = lane >> 2;
-    int ch = m * kHeadDim + (lane & 3) * 8;
     const float* sp = samp + (size_t)warp * kSampW;
-    const float* Vr = V + (size_t)row * N * kE + ch;
-    float4 o01 = *reinterpret_cast<const float4*>(sp + m * 8);
-    float4 o23 = *reinterpret_cast<const float4*>(sp + m * 8 + 4);
-    float4 aw = *reinterpret_cast<const float4*>(sp + 64 + m * 4);
-    float offx[4] = {o01.x, o01.z, o23.x, o23.z};
-    float offy[4] = {o01.y, o01.w, o23.y, o23.w};
-    float a[4] = {aw.x, aw.y, aw.z, aw.w};
     const float fW = (float)W, fH = (float)H;
     const float refx = __fdiv_rn((float)j + 0.5f, fW);
     const float refy = __fdiv_rn((float)i + 0.5f, fH);
-    float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int p = 0; p < kPoints; ++p) {
-        float lx = __fadd_rn(refx, __fdiv_rn(offx[p], fW));
-        float ly = __fadd_rn(refy, __fdiv_rn(offy[p], fH));
-        float gx = __fadd_rn(__fmul_rn(2.0f, lx), -1.0f);
-        float gy = __fadd_rn(__fmul_rn(2.0f, ly), -1.0f);
-        float x = __fadd_rn(__fmul_rn(__fadd_rn(gx, 1.0f), fW * 0.5f), -0.5f);
-        float y = __fadd_rn(__fmul_rn(__fadd_rn(gy, 1.0f), fH * 0.5f), -0.5f);
-        float xf = floorf(x), yf = floorf(y);
-        float wx1 = x - xf, wy1 = y - yf;
-        float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-        // guard against NaN/huge offsets before the int conversion
-        int x0 = (xf >= -2.0f && xf <= fW) ? (int)xf : -2;
-        int y0 = (yf >= -2.0f && yf <= fH) ? (int)yf : -2;
-        float s[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) s[c] = 0.f;
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy) {
-            int yy = y0 + cy;
-            if (yy < 0 || yy >= H) continue;
-            float wy = cy ? wy1 : wy0;
-#pragma unroll
-            for (int cx = 0; cx < 2; ++cx) {
-                int xx = x0 + cx;
-                if (xx < 0 || xx >= W) continue;
-                float wgt = wy * (cx ? wx1 : wx0);
-                const float* vp = Vr + (size_t)(yy * W + xx) * kE;
-                float4 v0 = __ldg(reinterpret_cast<const float4*>(vp));
-                float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + 4));
-                s[0] = fmaf(wgt, v0.x, s[0]); s[1] = fmaf(wgt, v0.y, s[1]);
-                s[2] = fmaf(wgt, v0.z, s[2]); s[3] = fmaf(wgt, v0.w, s[3]);
-                s[4] = fmaf(wgt, v1.x, s[4]); s[5] = fmaf(wgt, v1.y, s[5]);
-                s[6] = fmaf(wgt, v1.z, s[6]); s[7] = fmaf(wgt, v1.w, s[7]);
+    for (int hg = 0; hg < 2; ++hg) {
+        const int m = hg * 4 + (lane >> 3);
+        const int ch = m * kHeadDim + (lane & 7) * 4;
+        const float* Vr = V + (size_t)row * N * kE + ch;
+        const float4 o01 = *reinterpret_cast<const float4*>(sp + m * 8);
+        const float4 o23 = *reinterpret_cast<const float4*>(sp + m * 8 + 4);
+        const float4 aw = *reinterpret_cast<const float4*>(sp + 64 + m * 4);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        msda_point(Vr, o01.x, o01.y, aw.x, refx, refy, fW, fH, W, H, acc);
+        msda_point(Vr, o01.z, o01.w, aw.y, refx, refy, fW, fH, W, H, acc);
+        msda_point(Vr, o23.x, o23.y, aw.z, refx, refy, fW, fH, W, H, acc);
+        msda_point(Vr, o23.z, o23.w, aw.w, refx, refy, fW, fH, W, H, acc);
+        const size_t o = (size_t)warp * kE + ch;
+        if (out) *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (out_hi) {
+            __half2 h01, h23, l01, l23;
+            const float a0 = acc[0] * kSplitScale, a1 = acc[1] * kSplitScale, a2 = acc[2] * kSplitScale, a3 = acc[3] * kSplitScale;
+            h01 = __floats2half2_rn(a0, a1); h23 = __floats2half2_rn(a2, a3);
+            *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+            if (out_lo) {
+                const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+                l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y); l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+                *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
             }
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(a[p], s[c], acc[c]);
-    }
-    if (out) {
-        float* op = out + (size_t)warp * kE + ch;
-        *reinterpret_cast<float4*>(op) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(op + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    if (out_hi) {
-        size_t o = (size_t)warp * kE + ch;
-        split8_store(acc, out_hi + o, out_lo ? out_lo + o : nullptr);
     }
 }
 
