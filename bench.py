@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="cityscapes_512x1024_T10", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm", default=os.environ.get("DDP_GEMM", "fp32"))
+    ap.add_argument("--gemm", default=os.environ.get("DDP_GEMM", "tc_3xf16"), choices=["fp32", "tc_3xf16", "tc_f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-gpu", type=int, default=0, help="override images per GPU")
     args = ap.parse_args()
@@ -298,6 +298,13 @@ def main():
         achieved = by * tokens_per_launch / avg_s / 1e9
         roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None}
+    # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel class, from the committed capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(f"{args.workload}/{args.gemm}", {}).get(dname)
+        if t is not None and wl["per_gpu"] == WORKLOADS[args.workload]["per_gpu"]:
+            roof["traffic"] = t
+    roof["algorithmic_bytes"] = by * tokens_per_launch
     roof["avg_launch_ms"] = 1e3 * avg_s
     roof["launches_timed"] = dcount
     total_prof = sum(v[0] for v in prof.values())

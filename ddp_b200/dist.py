@@ -1,0 +1,49 @@
+"""Data parallelism of the decode loop: images are independent, so a batch is sharded across
+ranks (one process per GPU) with NO data-path collective, followed by ONE gather of the final logits.
+
+Replaces the reference's pickle-based ``collect_results_gpu`` (segmentation/mmseg/apis/test.py:229-232)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch, world_size, rank):
+    """Contiguous shard [lo, hi) of `batch` images for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(local, batch, group=None):
+    """All ranks receive the full (batch, ...) tensor, in image order.  NCCL: one all_gather_into_tensor when
+    shards are equal (the benchmarked case), otherwise a padded all_gather."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(batch, world, r) for r in range(world)]
+    counts = [hi - lo for lo, hi in sizes]
+    if len(set(counts)) == 1:
+        out = local.new_empty((batch,) + tuple(local.shape[1:]))
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        else:
+            dist.all_gather(list(out.chunk(world)), local.contiguous(), group=group)
+        return out
+    mx = max(counts)
+    pad = local.new_zeros((mx,) + tuple(local.shape[1:]))
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def distributed_sample(sample_fn, x, noise, group=None):
+    """Shard (x, noise) over the ranks of `group`, run `sample_fn(x_local, noise_local)` and gather the result.
+
+    `x` / `noise` hold the FULL batch on every rank (or at least this rank's shard rows)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(x.shape[0], world, rank)
+    out = sample_fn(x[lo:hi], noise[lo:hi])
+    if world == 1:
+        return out
+    return gather_results(out, x.shape[0], group)

@@ -1,0 +1,258 @@
+"""``DDP`` / ``SelfAlignedDDP`` segmentors — plug-in surface of the reference, hot path in libddp_b200.so.
+
+Reference: segmentation/mmseg/models/segmentors/ddp.py:49-290, self_aligned_ddp.py (inference identical),
+encoder_decoder.py:24-304, base.py:62-110.  Same constructor signature, methods and state-dict keys; the
+T-step loop (`ddim_sample`) is ONE call into the CUDA library instead of ~180 PyTorch launches per step.
+"""
+import warnings
+
+import weakref
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..engine import DecodeEngine
+from ..registry import SEGMENTORS, MODELS, build_head
+
+EMBED = 256
+
+
+def resize(input, size=None, scale_factor=None, mode="nearest", align_corners=None, warning=True):
+    """segmentation/mmseg/ops/wrappers.py:8-27."""
+    return F.interpolate(input, size, scale_factor, mode, align_corners)
+
+
+class LearnedSinusoidalPosEmb(nn.Module):
+    """Parameter container of ddp.py:31-46 (key ``time_mlp.0.weights``)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        assert (dim % 2) == 0
+        self.weights = nn.Parameter(torch.randn(dim // 2))
+
+
+class _ConvModule1x1(nn.Module):
+    """mmcv ConvModule(k=1, no norm, no act): key ``<name>.conv.{weight,bias}`` (ddp.py:92-100)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, 1, padding=0)
+
+
+class _MissingEncoder(nn.Module):
+    """Placeholder for a backbone / neck type that is not registered here (the encoder is outside the hot path)."""
+
+    def __init__(self, type, **kw):
+        super().__init__()
+        self.missing_type = type
+
+    def forward(self, *a, **k):
+        raise RuntimeError(f"encoder module '{self.missing_type}' is not available in ddp_b200 (out of scope): "
+                           "register it in ddp_b200.registry.MODELS, run inside mmseg, or pass neck features to ddim_sample")
+
+
+def _build_encoder_part(cfg):
+    if cfg is None:
+        return None
+    if isinstance(cfg, (list, tuple)):
+        return nn.Sequential(*[_build_encoder_part(c) for c in cfg])
+    typ = cfg.get("type")
+    if isinstance(typ, str) and typ not in MODELS:
+        warnings.warn(f"'{typ}' is not registered; using a placeholder (the encoder is outside the ddp_b200 hot path)")
+        return _MissingEncoder(**cfg)
+    return MODELS.build(cfg)
+
+
+class _DiffusionSegmentorBase(nn.Module):
+    """EncoderDecoder surface shared by the seg and depth plug-ins."""
+
+    engine_task = "seg"
+
+    def _init_encoder(self, backbone, neck, pretrained):
+        if pretrained is not None:
+            assert backbone.get("pretrained") is None, "both backbone and segmentor set pretrained weight"
+        self.backbone = _build_encoder_part(backbone)
+        if neck is not None:
+            self.neck = _build_encoder_part(neck)
+
+    @property
+    def with_neck(self):
+        return hasattr(self, "neck") and self.neck is not None
+
+    def extract_feat(self, img):
+        x = self.backbone(img)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+    # ---- engine management -----------------------------------------------------------------
+    def _hot_state_dict(self):
+        return {k: v for k, v in self.state_dict().items()
+                if not k.startswith(("backbone.", "neck.", "auxiliary_head."))}
+
+    def _engine_kwargs(self):
+        raise NotImplementedError
+
+    def engine(self) -> DecodeEngine:
+        """The CUDA decode engine bound to the current parameters (rebuilt after load_state_dict / refresh)."""
+        if self._engine is None:
+            eng = DecodeEngine(gemm_mode=self.gemm_mode, **self._engine_kwargs())
+            eng.load_state_dict(self._hot_state_dict())
+            self._engine = eng
+        return self._engine
+
+    def refresh_engine(self):
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.refresh_engine()
+        return out
+
+    def _apply(self, fn, *a, **k):          # .cuda() / .to(): parameters moved, engine re-reads them lazily
+        self.refresh_engine()
+        return super()._apply(fn, *a, **k)
+
+    def forward_train(self, *a, **k):
+        raise NotImplementedError("training is outside the scope of ddp_b200 (inference hot path only)")
+
+    def forward(self, img, img_metas, return_loss=False, **kwargs):
+        """base.py:96-110."""
+        if return_loss:
+            return self.forward_train(img, img_metas, **kwargs)
+        return self.forward_test(img, img_metas, **kwargs)
+
+    def forward_test(self, imgs, img_metas, **kwargs):
+        """base.py:62-94 (single-augmentation path; aug_test averages `inference` outputs)."""
+        for var, name in [(imgs, "imgs"), (img_metas, "img_metas")]:
+            if not isinstance(var, list):
+                raise TypeError(f"{name} must be a list, but got {type(var)}")
+        if len(imgs) != len(img_metas):
+            raise ValueError(f"num of augmentations ({len(imgs)}) != num of image meta ({len(img_metas)})")
+        if len(imgs) == 1:
+            return self.simple_test(imgs[0], img_metas[0], **kwargs)
+        return self.aug_test(imgs, img_metas, **kwargs)
+
+
+@SEGMENTORS.register_module()
+class DDP(_DiffusionSegmentorBase):
+    def __init__(self, bit_scale=0.1, timesteps=1, randsteps=1, time_difference=1, learned_sinusoidal_dim=16,
+                 sample_range=(0, 0.999), noise_schedule="cosine", diffusion="ddim", accumulation=False,
+                 backbone=None, decode_head=None, neck=None, auxiliary_head=None, train_cfg=None, test_cfg=None,
+                 pretrained=None, init_cfg=None, gemm_mode="tc_3xf16"):
+        super().__init__()
+        self._engine = None
+        self.gemm_mode = gemm_mode
+        self._init_encoder(backbone, neck, pretrained)
+        self.decode_head = build_head(decode_head)
+        self.decode_head.__dict__['_owner'] = weakref.ref(self)     # not a submodule: no cycle in state_dict
+        self.align_corners = self.decode_head.align_corners
+        self.num_classes = self.decode_head.num_classes
+        self.out_channels = self.decode_head.out_channels
+        # the auxiliary head only matters for training (deep supervision); its config is accepted and ignored
+        self.auxiliary_head_cfg = auxiliary_head
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+
+        self.bit_scale = bit_scale
+        self.timesteps = timesteps
+        self.randsteps = randsteps
+        self.diffusion = diffusion
+        self.time_difference = time_difference
+        self.sample_range = sample_range
+        self.use_gt = False
+        self.accumulation = accumulation
+        self.learned_sinusoidal_dim = learned_sinusoidal_dim
+        self.embedding_table = nn.Embedding(self.num_classes + 1, self.decode_head.in_channels[0])
+        print(f" timesteps: {timesteps}, randsteps: {randsteps}, sample_range: {sample_range}, diffusion: {diffusion}")
+        if noise_schedule not in ("linear", "cosine"):
+            raise ValueError(f"invalid noise schedule {noise_schedule}")
+        self.noise_schedule = noise_schedule
+        c = self.decode_head.in_channels[0]
+        if c != EMBED:
+            raise NotImplementedError("libddp_b200 is built for 256-channel neck features")
+        self.transform = _ConvModule1x1(c * 2, c)
+        time_dim = c * 4
+        self.time_mlp = nn.Sequential(LearnedSinusoidalPosEmb(learned_sinusoidal_dim),
+                                      nn.Linear(learned_sinusoidal_dim + 1, time_dim), nn.GELU(),
+                                      nn.Linear(time_dim, time_dim))
+
+    def _engine_kwargs(self):
+        return dict(task="seg", num_classes=self.num_classes, timesteps=self.timesteps,
+                    time_difference=self.time_difference, sample_range=self.sample_range,
+                    noise_schedule=self.noise_schedule, diffusion="ddim", accumulation=self.accumulation,
+                    bit_scale=self.bit_scale, learned_sinusoidal_dim=self.learned_sinusoidal_dim,
+                    num_layers=self.decode_head.encoder.num_layers)
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    def encode_decode(self, img, img_metas):
+        """ddp.py:114-129."""
+        x = self.extract_feat(img)[0]
+        if self.diffusion == "ddim":
+            out = self.ddim_sample(x, img_metas)
+        elif self.diffusion == "ddpm":
+            out = self.ddpm_sample(x, img_metas)
+        else:
+            raise NotImplementedError
+        return resize(input=out, size=img.shape[2:], mode="bilinear", align_corners=self.align_corners)
+
+    @torch.no_grad()
+    def ddim_sample(self, x, img_metas=None, noise=None):
+        """ddp.py:215-246, batched: x (b,256,h,w) -> (b,C,h,w).  The reference loop is only defined for b=1
+        (its batch axis is ``randsteps``); here every image gets its own ``randsteps`` samples and its own mean.
+        ``noise`` (b, randsteps, 256, h, w) may be given; otherwise it is drawn like ddp.py:220 does."""
+        b, c, h, w = x.shape
+        if noise is None:
+            noise = torch.randn((b, self.randsteps, c, h, w), device=x.device)
+        return self.engine().sample(x.float(), noise)
+
+    def ddpm_sample(self, x, img_metas=None):
+        raise NotImplementedError("diffusion='ddpm' (ddp.py:248-290) is not built; no shipped config uses it")
+
+    def _head_forward(self, feat, times):
+        raise NotImplementedError("single denoiser calls (decode_head.forward) are not exported by libddp_b200 yet; "
+                                  "the sampling loop is (ddim_sample)")
+
+    def _decode_head_forward_test(self, x, t, img_metas):
+        return self.decode_head.forward_test(x, t, img_metas, self.test_cfg)
+
+    # ---- callers of the hot path (encoder_decoder.py:229-304) -------------------------------------
+    def whole_inference(self, img, img_meta, rescale):
+        seg_logit = self.encode_decode(img, img_meta)
+        if rescale:
+            resize_shape = img_meta[0]["img_shape"][:2]
+            seg_logit = seg_logit[:, :, :resize_shape[0], :resize_shape[1]]
+            size = img_meta[0]["ori_shape"][:2]
+            seg_logit = resize(seg_logit, size=size, mode="bilinear", align_corners=self.align_corners, warning=False)
+        return seg_logit
+
+    def inference(self, img, img_meta, rescale):
+        mode = (self.test_cfg or {}).get("mode", "whole")
+        assert mode in ["slide", "whole"]
+        if mode == "slide":
+            raise NotImplementedError("slide inference is not used by any DDP config")
+        seg_logit = self.whole_inference(img, img_meta, rescale)
+        output = F.softmax(seg_logit, dim=1)
+        if img_meta[0].get("flip", False):
+            flip_direction = img_meta[0]["flip_direction"]
+            assert flip_direction in ["horizontal", "vertical"]
+            output = output.flip(dims=(3,)) if flip_direction == "horizontal" else output.flip(dims=(2,))
+        return output
+
+    def simple_test(self, img, img_meta, rescale=True):
+        seg_logit = self.inference(img, img_meta, rescale)
+        seg_pred = seg_logit.argmax(dim=1)
+        return list(seg_pred.cpu().numpy())
+
+    def aug_test(self, imgs, img_metas, rescale=True):
+        assert rescale
+        seg_logit = self.inference(imgs[0], img_metas[0], rescale)
+        for i in range(1, len(imgs)):
+            seg_logit += self.inference(imgs[i], img_metas[i], rescale)
+        seg_logit /= len(imgs)
+        return list(seg_logit.argmax(dim=1).cpu().numpy())
+
+
+@SEGMENTORS.register_module()
+class SelfAlignedDDP(DDP):
+    """self_aligned_ddp.py: differs from DDP only in forward_train (lines 148-175); inference is the same kernel."""

@@ -241,3 +241,99 @@ def test_library_schedule_close_to_reference_schedule():
         b = DecodeEngine(num_classes=19, timesteps=T, host_schedule=True).get_schedule()
         for col_a, col_b in zip(a, b):
             assert np.allclose(col_a, col_b, rtol=2e-5, atol=2e-6), (col_a, col_b)
+
+
+# ------------------------------------------------------------------------------------------------
+# through the plug-in classes (the reference-facing surface)
+# ------------------------------------------------------------------------------------------------
+def _toy_model(timesteps=3, randsteps=1, **over):
+    import warnings
+    from ddp_b200.config import Config
+    from ddp_b200.registry import build_segmentor
+    import test_plugin_cpu  # noqa: F401  (registers ToyBackbone)
+    cfg = Config.fromfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "ddp_toy_config.py"))
+    m = dict(cfg.model)
+    m.update(timesteps=timesteps, randsteps=randsteps, **over)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return build_segmentor(m)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_plugin_ddim_sample_matches_oracle(mode):
+    model = _toy_model(timesteps=3, randsteps=2, gemm_mode=mode)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3, randsteps=2)
+    W = O.make_weights(cfg, seed=9)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    x, noise = O.make_inputs(cfg, 2, 12, 20, seed=21)
+    out = model.ddim_sample(x.cuda(), None, noise=noise.cuda()).cpu()
+    ref = O.sample(W, cfg, x, noise)
+    assert (out - ref).abs().max().item() < ATOL
+    assert argmax_report(out, ref)[0] == 0
+    # noise drawn inside, like ddp.py:220
+    torch.manual_seed(5)
+    out2 = model.ddim_sample(x.cuda(), None)
+    torch.manual_seed(5)
+    drawn = torch.randn((2, 2, 256, 12, 20), device="cuda")
+    ref2 = O.sample(W, cfg, x, drawn.cpu())
+    assert argmax_report(out2.cpu(), ref2)[0] == 0
+
+
+def test_plugin_simple_test_end_to_end():
+    """img -> (toy) encoder -> ddim loop in the library -> x4 bilinear resize -> softmax -> argmax -> numpy,
+    i.e. BaseSegmentor.forward(return_loss=False) as tools/test.py calls it."""
+    model = _toy_model(timesteps=2)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    W = O.make_weights(cfg, seed=12)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    img = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    metas = [dict(img_shape=(64, 96, 3), ori_shape=(64, 96, 3), pad_shape=(64, 96, 3), flip=False)]
+    torch.manual_seed(77)
+    pred = model(img=[img], img_metas=[metas], return_loss=False)
+    assert isinstance(pred, list) and pred[0].shape == (64, 96)
+    with torch.no_grad():
+        x = model.extract_feat(img)[0]
+    torch.manual_seed(77)
+    noise = torch.randn((1, 1, 256, 16, 24), device="cuda")
+    logits = O.sample(W, cfg, x.cpu(), noise.cpu())
+    up = torch.nn.functional.interpolate(logits, size=(64, 96), mode="bilinear", align_corners=False)
+    want = up.softmax(1).argmax(1)[0].numpy()
+    assert (pred[0] != want).sum() == 0
+
+
+def test_plugin_depth_sample_matches_oracle():
+    from ddp_b200.registry import build_depther
+    import test_plugin_cpu  # noqa: F401
+    dh = dict(type="DeformableHeadWithTime", in_channels=[256], channels=256, in_index=[0], dropout_ratio=0.,
+              min_depth=1e-3, max_depth=10, num_feature_levels=1,
+              encoder=dict(type="DetrTransformerEncoder", num_layers=6, transformerlayers=dict(
+                  type="BaseTransformerLayer", use_time_mlp=True,
+                  attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1, num_heads=8, dropout=0.),
+                  ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, ffn_drop=0., act_cfg=dict(type="GELU")),
+                  operation_order=("self_attn", "norm", "ffn", "norm"))),
+              positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True, offset=-0.5))
+    model = build_depther(dict(type="DDP", bit_scale=0.1, timesteps=4, min_depth=1e-3, max_depth=10,
+                               backbone=dict(type="ToyBackbone"), decode_head=dh))
+    cfg = O.OracleConfig(task="depth", timesteps=4, bit_scale=0.1)
+    W = O.make_weights(cfg, seed=14)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    x, noise = O.make_inputs(cfg, 2, 10, 12, seed=22)
+    out = model.sample(x.cuda(), None, noise=noise.cuda()).cpu()
+    ref = O.sample(W, cfg, x, noise)
+    assert (out - ref).abs().max().item() < 1e-3
+
+
+def test_fast_mode_reports_mismatch_rate():
+    """DDP_GEMM_TC_F16 (one fp16 MMA per product) is NOT parity-grade: it must stay close, and we record how close."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3)
+    W = O.make_weights(cfg, seed=31)
+    x, noise = O.make_inputs(cfg, 2, 32, 48, seed=78)
+    ref = O.sample(W, cfg, x, noise)
+    out = make_engine(cfg, W, "tc_f16").sample(x.cuda(), noise.cuda()).cpu()
+    bad, tot = argmax_report(out, ref)
+    d = (out - ref).abs().max().item()
+    print(f"tc_f16: max|d|={d:.3e}, class-map mismatches {bad}/{tot}")
+    assert d < 0.1 and bad / tot < 0.02

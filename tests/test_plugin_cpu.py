@@ -1,0 +1,149 @@
+"""Host-side logic of the drop-in boundary (no GPU): config loader, registry, plug-in classes' constructor
+surface and state-dict keys, sharding + gather over a world_size-2 gloo group."""
+import glob
+import os
+import warnings
+
+import pytest
+import torch
+
+from ddp_b200.config import Config
+from ddp_b200.registry import MODELS, build_segmentor, build_depther
+import ddp_b200.models as M
+from ddp_b200 import dist as D
+from oracle import ddp_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+@MODELS.register_module(name="ToyBackbone", force=True)
+class ToyBackbone(torch.nn.Module):
+    """Produces a 1/stride-resolution 256-channel map (stands in for backbone + FPN + MultiStageMerging)."""
+
+    def __init__(self, channels=256, stride=4):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, channels, stride, stride=stride)
+
+    def forward(self, img):
+        return [self.conv(img)]
+
+
+def test_config_loader_base_and_delete():
+    cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
+    assert cfg.model.type == "DDP" and cfg.model.decode_head.encoder.num_layers == 6
+    assert cfg.dist_params.backend == "nccl"                      # inherited from _base_
+    assert cfg.optimizer == dict(type="AdamW", lr=0.00006, betas=(0.9, 0.999), weight_decay=0.01)   # _delete_
+    assert cfg.log_config.hooks[0].type == "TextLoggerHook"
+
+
+def test_build_from_config_and_state_dict_keys_match_reference():
+    cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = build_segmentor(cfg.model)
+    assert isinstance(model, M.DDP) and model.num_classes == 19 and model.align_corners is False
+    assert model.decode_head.in_channels[0] == 256 and model.decode_head.out_channels == 19
+    want = O.make_weights(O.OracleConfig(task="seg", num_classes=19), seed=0)      # the reference's own keys/shapes
+    got = model._hot_state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+    model.load_state_dict(want, strict=False)
+    assert torch.equal(model.state_dict()["decode_head.encoder.layers.3.ffns.0.layers.1.weight"],
+                       want["decode_head.encoder.layers.3.ffns.0.layers.1.weight"])
+
+
+def test_depth_plugin_keys():
+    dh = dict(type="DeformableHeadWithTime", in_channels=[256], channels=256, in_index=[0], dropout_ratio=0.,
+              min_depth=1e-3, max_depth=10, num_feature_levels=1,
+              encoder=dict(type="DetrTransformerEncoder", num_layers=6, transformerlayers=dict(
+                  type="BaseTransformerLayer", use_time_mlp=True,
+                  attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1, num_heads=8, dropout=0.),
+                  ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, ffn_drop=0., act_cfg=dict(type="GELU")),
+                  operation_order=("self_attn", "norm", "ffn", "norm"))),
+              positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True, offset=-0.5))
+    model = build_depther(dict(type="DDP", bit_scale=0.1, timesteps=3, min_depth=1e-3, max_depth=10,
+                               backbone=dict(type="ToyBackbone"), decode_head=dh))
+    want = O.make_weights(O.OracleConfig(task="depth"), seed=0)
+    got = model._hot_state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+
+
+def test_constructor_errors_mirror_reference():
+    cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
+    bad = dict(cfg.model)
+    bad["noise_schedule"] = "quadratic"
+    with pytest.raises(ValueError, match="invalid noise schedule"):       # ddp.py:90
+        build_segmentor(bad)
+    bad = dict(cfg.model)
+    bad["decode_head"] = dict(cfg.model.decode_head, positional_encoding=dict(type="SinePositionalEncoding", num_feats=64,
+                                                                               normalize=True, offset=-0.5))
+    with pytest.raises(AssertionError, match="embed_dims should be exactly 2 times"):   # deformable_head_with_time.py:45-47
+        build_segmentor(bad)
+    with pytest.raises(KeyError):
+        build_segmentor(dict(type="NoSuchSegmentor"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_reference_config_files_build_unchanged():
+    files = sorted(glob.glob(f"{REF}/segmentation/configs/*/ddp_*.py"))
+    assert len(files) == 14
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f in files:
+            cfg = Config.fromfile(f)
+            model = build_segmentor(cfg.model)
+            assert type(model).__name__ == cfg.model.type
+            assert model.timesteps == cfg.model.timesteps and model.bit_scale == 0.01
+        dfiles = sorted(glob.glob(f"{REF}/depth/configs/ddp_*/*.py"))
+        assert len(dfiles) == 8
+        for f in dfiles:
+            cfg = Config.fromfile(f)
+            model = build_depther(cfg.model)
+            assert model.max_depth == cfg.model.max_depth
+
+
+def test_shard_bounds_cover_batch():
+    for B in (1, 5, 8, 64):
+        for W in (1, 2, 3, 8):
+            spans = [D.shard_bounds(B, W, r) for r in range(W)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, batch, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(batch, 4, 3, 5, generator=g)
+        noise = torch.randn(batch, 2, 4, 3, 5, generator=g)
+
+        def fake_sample(xl, nl):                 # stands in for engine.sample on this rank's shard
+            return xl * 2 + nl.mean(1)
+        out = D.distributed_sample(fake_sample, x, noise)
+        q.put((rank, torch.equal(out, x * 2 + noise.mean(1)), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [4, 5])
+def test_two_rank_gloo_shard_and_gather(batch):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29511 + batch
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (batch, 4, 3, 5) for _, _, shape in res)
