@@ -419,6 +419,12 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
 }
 
 
+bool has_tap(const ddp_handle* h, int kind, int step, int layer) {
+    for (const Tap& t : h->taps)
+        if (t.kind == kind && t.step == step && (layer < 0 || t.layer == layer)) return true;
+    return false;
+}
+
 int do_tap(ddp_handle* h, int kind, int step, int layer, const float* src, size_t nfloats, cudaStream_t st) {
     for (const Tap& t : h->taps) {
         if (t.kind == kind && t.step == step && (t.layer == layer || layer < 0)) {
@@ -430,6 +436,7 @@ int do_tap(ddp_handle* h, int kind, int step, int layer, const float* src, size_
 
 struct Workspace {
     float *cond, *state, *q, *V, *samp, *g, *hid, *logits, *accum, *pred;
+    uint32_t* rec;          // [rows][N][kRecW] resolved sampling records
     __half *state_hi, *state_lo, *q_hi, *q_lo, *g_hi, *g_lo, *hid_hi, *hid_lo;    // tcgen05 path: fp16 planes
     float *stage_x, *stage_noise, *stage_out;
     int32_t* stage_cls;
@@ -452,6 +459,7 @@ size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_byt
     w.q = b.take(rows * N * kE);
     w.V = b.take(rows * N * kE);
     w.samp = b.take(rows * N * kSampW);
+    w.rec = reinterpret_cast<uint32_t*>(b.take(rows * N * kRecW));
     w.g = b.take(rows * N * kE);        // tcgen05 path: only written when a GATHERED tap is registered
     if (!h->tc) {
         w.hid = b.take(rows * N * kFFN);
@@ -696,7 +704,8 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     if (!h) return DDP_ERR_INVALID;
     if (!h->committed) return fail(h, DDP_ERR_STATE, "ddp_plan: call ddp_commit_weights first");
     if (B < 1 || R < 1 || height < 1 || width < 1) return fail(h, DDP_ERR_INVALID, "ddp_plan: B, R, h, w must be >= 1");
-    if ((long long)B * R * height * width > (1ll << 30)) return fail(h, DDP_ERR_INVALID, "ddp_plan: too many tokens");
+    if ((long long)B * R * height * width > (1ll << 30) || (long long)height * width >= (1ll << 26))
+        return fail(h, DDP_ERR_INVALID, "ddp_plan: too many tokens");
     CUDA_TRY(h, cudaSetDevice(h->device));
     const ddp_config& c = h->cfg;
     const int T = c.timesteps, Lc = c.num_layers, N = height * width;
@@ -814,7 +823,7 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
         // head input tokens q = cond + W_m m_t
         if (seg && h->tc) {
             tc::EpiParams ep{};
-            ep.scale = h->tc_in.inv_scale; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+            ep.scale = h->tc_in.inv_scale; ep.out = has_tap(h, DDP_TAP_HEAD_IN, k, -1) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
             ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
             ep.cond = ws.cond; ep.N_tok = N; ep.R = R;
             TC_GEMM(h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, h->mA_state, h->tc_in, M, kE, ep);
@@ -842,20 +851,23 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                 }
                 {   // offsets / attention weights = proj(q + pos) = q W^T + pew
                     tc::EpiParams ep{};
-                    ep.scale = T.s.inv_scale; ep.out = ws.samp; ep.ldc = kSampW; ep.ncols = kSampW; ep.pew = h->pew[j]; ep.N_tok = N;
+                    bool want_s = false;
+                    for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
+                    ep.scale = T.s.inv_scale; ep.out = want_s ? ws.samp : nullptr; ep.ldc = kSampW; ep.ncols = kSampW;
+                    ep.pew = h->pew[j]; ep.N_tok = N; ep.rec = ws.rec; ep.H = h->H; ep.W = h->W;
                     TC_GEMM(h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
                 }
                 if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
-                if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
+                if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;   // written only when tapped
                 bool want_g = false;
                 for (const Tap& t : h->taps) want_g = want_g || (t.kind == DDP_TAP_GATHERED && t.step == k && t.layer == j);
                 KLAUNCH(h, DDP_K_GATHER, st,
                         (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
-                            ws.V, ws.samp, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, h->H, h->W, M)));
+                            ws.V, ws.rec, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, N, h->W, M)));
                 if (want_g && (rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
                 {   // q = LN1(q + output_proj(g))
                     tc::EpiParams ep{};
-                    ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+                    ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = has_tap(h, DDP_TAP_LN1, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
                     ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                     ep.ln_g = L.g1; ep.ln_b = L.e1;
                     TC_GEMM2(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
@@ -869,7 +881,7 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                 }
                 {   // q = FiLM(LN2(q + hid W2^T + b2))
                     tc::EpiParams ep{};
-                    ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = ws.q; ep.ldc = kE; ep.ncols = kE;
+                    ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
                     ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                     ep.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; ep.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
                     TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
@@ -880,13 +892,13 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                 KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
             }
             {   // offsets / attention weights = proj(q + pos) = q W^T + pew
-                EpiSampling epi{ws.samp, h->pew[j], N, M};
+                EpiSampling epi{ws.samp, ws.rec, h->pew[j], N, h->H, h->W, M};
                 KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
             }
             if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
             if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
             KLAUNCH(h, DDP_K_GATHER, st,
-                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.samp, ws.g, nullptr, nullptr, h->H, h->W, M)));
+                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.rec, ws.g, nullptr, nullptr, N, h->W, M)));
             if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
             {   // q = LN1(q + output_proj(g))
                 EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};

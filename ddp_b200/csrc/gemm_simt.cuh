@@ -66,7 +66,9 @@ struct EpiAddCond {
 // softmax over each head's 4 points for cols 64..95 (vmmcv/ops/multi_scale_deform_attn.py:319-328).
 // BN == 128: lane tx holds exactly one group of 4 consecutive columns.
 struct EpiSampling {
-    float* out; const float* pew; int N; int M;
+    float* out;            // optional [M][96] offsets | softmaxed weights (test tap), may be null
+    uint32_t* rec;         // [M][kRecW] sampling records consumed by k_msda_gather
+    const float* pew; int N; int H; int W; int M;
     template <int TM, int TN>
     __device__ __forceinline__ void operator()(float (&acc)[TM][TN], int grow0, int tx, int n0) const {
         static_assert(TN == 4, "EpiSampling needs BN == 128");
@@ -79,13 +81,26 @@ struct EpiSampling {
             int n = row % N;
             float4 pv = *reinterpret_cast<const float4*>(pew + (size_t)n * kSampW + col);
             float v0 = acc[r][0] + pv.x, v1 = acc[r][1] + pv.y, v2 = acc[r][2] + pv.z, v3 = acc[r][3] + pv.w;
+            uint32_t* rp = rec + (size_t)row * kRecW;
             if (col >= 64) {
                 float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
                 v0 = expf(v0 - mx); v1 = expf(v1 - mx); v2 = expf(v2 - mx); v3 = expf(v3 - mx);
                 float s = (v0 + v1) + (v2 + v3);
                 v0 /= s; v1 /= s; v2 /= s; v3 /= s;
+                *reinterpret_cast<float4*>(rp + 96 + (col - 64)) = make_float4(v0, v1, v2, v3);
+            } else {
+                // columns col..col+3 = (x, y) offsets of sampling points k = col/2 and k+1
+                const int i = n / W, j = n - i * W, k = col >> 1;
+                const float refx = __fdiv_rn((float)j + 0.5f, (float)W), refy = __fdiv_rn((float)i + 0.5f, (float)H);
+                const float rW = __frcp_rn((float)W), rH = __frcp_rn((float)H);
+                uint32_t w0, w1; float fx0, fy0, fx1, fy1;
+                msda_resolve(v0, v1, refx, refy, rW, rH, H, W, w0, fx0, fy0);
+                msda_resolve(v2, v3, refx, refy, rW, rH, H, W, w1, fx1, fy1);
+                *reinterpret_cast<uint2*>(rp + k) = make_uint2(w0, w1);
+                *reinterpret_cast<float2*>(rp + 32 + k) = make_float2(fx0, fx1);
+                *reinterpret_cast<float2*>(rp + 64 + k) = make_float2(fy0, fy1);
             }
-            *reinterpret_cast<float4*>(out + (size_t)row * kSampW + col) = make_float4(v0, v1, v2, v3);
+            if (out) *reinterpret_cast<float4*>(out + (size_t)row * kSampW + col) = make_float4(v0, v1, v2, v3);
         }
     }
 };

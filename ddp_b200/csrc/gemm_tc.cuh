@@ -211,6 +211,21 @@ __device__ __forceinline__ void stage_store_f16(float* stg, const uint4* h, __ha
     }
     __syncwarp();
 }
+// 32 rows x 32 fp16 columns (64-byte rows) through a 2 KB tile: `h` = the row's 32 halves packed as 4 uint4
+__device__ __forceinline__ void stage_store_f16_32(float* stg, const uint4* h, __half* dst, int ld, int rows_valid, int lane) {
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s16[lane * 4 + (j ^ ((lane >> 1) & 3))] = h[j];
+    __syncwarp();
+    const int c = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (lane >> 2) + 8 * i;
+        uint4 x = s16[r * 4 + (c ^ ((r >> 1) & 3))];
+        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c * 8) = x;
+    }
+    __syncwarp();
+}
 // fp16 planes of kActScale * v[0..63]; lo plane skipped when NSPLIT == 1
 template <int NSPLIT>
 __device__ __forceinline__ void split_store64(float* stg, const float (&v)[64], const SplitOut& o, size_t row0, int col,
@@ -244,7 +259,7 @@ struct EpiParams {
     // EPI_ADD_COND
     const float* cond; int N_tok; int R;
     // EPI_SAMPLING
-    const float* pew;
+    const float* pew; uint32_t* rec; int H; int W;
     // EPI_RES_LN: y = LN(acc*scale + bias) * g + b; the residual is part of the accumulator (identity block of W),
     // g / b already carry the FiLM (scale+1), shift
     const float* ln_g; const float* ln_b;
@@ -257,40 +272,44 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;
-constexpr int kThreadsTc = 32 * (2 + kEpiWarps);
-constexpr int kStageTileBytes = 4096;        // per-warp store staging tile
+constexpr int kStageAreaBytes = 32768;       // store staging tiles of all epilogue warps
+__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_GELU ? 16 : 8; }    // the GELU epilogue is issue-bound: 16 warps
+__host__ __device__ constexpr int tc_threads(int epi) { return 32 * (2 + epi_warps(epi)); }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int EPI = EPI_BIAS>
 struct Cfg {
+    static constexpr int kEpiWarps = epi_warps(EPI);
+    static constexpr int kStageTileBytes = kStageAreaBytes / kEpiWarps;
     static constexpr int kABytes = BM * BK * 2;               // one fp16 plane of an A stage
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = NSPLIT == 1 ? (kABytes + kBBytes) : 2 * (kABytes + kBBytes);
     static constexpr int kStages = (192 * 1024 / kStageBytes) > 6 ? 6 : (192 * 1024 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static constexpr int kEpiActive = BN >= 128 ? 8 : 4;      // epilogue warps that take part
-    static constexpr int kColsPerWarp = BN >= 128 ? BN / 2 : BN;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStageTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiActive = EPI == EPI_GELU ? 16 : (BN >= 128 ? 8 : 4);      // epilogue warps that take part
+    static constexpr int kColsPerWarp = EPI == EPI_GELU ? BN / 4 : (BN >= 128 ? BN / 2 : BN);
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStageAreaBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(EPI != EPI_GELU || BN == 256, "the 16-warp GELU epilogue assumes 64 columns per warp");
     static_assert(kStages >= 2, "need at least two stages");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of sm_100");
 };
 
 template <int BN, int NSPLIT, int EPI>
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapA2hi, const __grid_constant__ CUtensorMap mapA2lo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                int M, int K, int K1, int n_tiles_n, EpiParams ep) {
     // A is the K-concatenation [A (K1 columns) | A2 (K - K1 columns)]: the residual of a post-norm block rides
     // along as extra K against a scaled identity block of W, so the epilogue never reads it from global memory.
-    using C = Cfg<BN, NSPLIT>;
+    using C = Cfg<BN, NSPLIT, EPI>;
+    constexpr int kStageTileBytes = C::kStageTileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (128B swizzle) by pointer arithmetic on the shared array, so that the compiler keeps
     // the shared address space (LDS/STS instead of generic accesses) for the staging tiles
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_tiles = smem + C::kStages * C::kStageBytes;
-    uint8_t* misc = stage_tiles + kEpiWarps * kStageTileBytes;
+    uint8_t* misc = stage_tiles + kStageAreaBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tfull_bar = empty_bar + C::kStages;     // [2] accumulator ready
@@ -387,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // ===================== epilogue: thread = row, 64-column chunks =====================
         const int ew = warp - 2;
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                                // which half of the tile's columns
+        const int half = ew >> 2;                                // which part (half, or quarter for GELU) of the tile's columns
         const int cbeg = half * C::kColsPerWarp;
         float* stg = reinterpret_cast<float*>(stage_tiles + ew * kStageTileBytes);
         int acc = 0; uint32_t acc_phase = 0;
@@ -460,12 +479,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         v[i * 4 + 2] = fmaf((v[i * 4 + 2] - mean) * rstd, g4.z, b4.z);
                         v[i * 4 + 3] = fmaf((v[i * 4 + 3] - mean) * rstd, g4.w, b4.w);
                     }
-                    float* dst = ep.out + (size_t)wrow0 * ep.ldc + c;
-                    stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
-                    stage_store_f32(stg, &v[32], dst + 32, ep.ldc, rows_valid, lane);
+                    if (ep.out) {                     // fp32 copy only when someone reads it (tests tap it); the planes carry the data
+                        float* dst = ep.out + (size_t)wrow0 * ep.ldc + c;
+                        stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
+                        stage_store_f32(stg, &v[32], dst + 32, ep.ldc, rows_valid, lane);
+                    }
                     if (ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, c, rows_valid, lane);
                 }
                 named_bar_sync(1 + q, 64);        // the partner may write the next tile's partials into this tile only now
+            } else if (EPI == EPI_GELU) {
+                // 16 warps x 64 columns, in two 32-column rounds; everything in the 16x-scaled domain of the fp16 planes:
+                // z16 = 16 (acc*scale + bias); planes of gelu(z) * 16 = z16 * Phi(z16 / 16)
+                const float s16 = ep.scale * kActScale;
+#pragma unroll 1
+                for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 32) {
+                    float v[32];
+                    tmem_ld32(t_row + c, v);
+                    const int col0 = n0 + c;
+                    uint4 hi[4], lo[4];
+                    __half2* h2 = reinterpret_cast<__half2*>(hi);
+                    __half2* l2 = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i * 4));
+                        float g[4];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float z16 = fmaf(v[i * 4 + e], s16, bb[e] * kActScale);
+                            const float u = fabsf(z16) * (0.70710678118654752440f * kInvActScale);
+                            float t, ex;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+                            float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+                            p = fmaf(p, t, 0.5f * 1.421413741f);
+                            p = fmaf(p, t, 0.5f * -0.284496736f);
+                            p = fmaf(p, t, 0.5f * 0.254829592f);
+                            p *= t;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u * u * -1.44269504088896340736f));
+                            const float hh = p * ex;
+                            g[e] = z16 * (z16 < 0.f ? hh : 1.0f - hh);
+                        }
+                        const __half2 h01 = __floats2half2_rn(g[0], g[1]), h23 = __floats2half2_rn(g[2], g[3]);
+                        h2[i * 2] = h01; h2[i * 2 + 1] = h23;
+                        if (NSPLIT > 1) {
+                            const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+                            l2[i * 2] = __floats2half2_rn(g[0] - b01.x, g[1] - b01.y);
+                            l2[i * 2 + 1] = __floats2half2_rn(g[2] - b23.x, g[3] - b23.y);
+                        }
+                    }
+                    stage_store_f16_32(stg, hi, ep.split.hi + (size_t)wrow0 * ep.split.ld + col0, ep.split.ld, rows_valid, lane);
+                    if (NSPLIT > 1)
+                        stage_store_f16_32(stg, lo, ep.split.lo + (size_t)wrow0 * ep.split.ld + col0, ep.split.ld, rows_valid, lane);
+                }
             } else {
 #pragma unroll 1
                 for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {
@@ -497,6 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                                 v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, p4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, p4.w);
                             }
                         }
+                        float* recf = reinterpret_cast<float*>(ep.rec + (size_t)wrow0 * kRecW);
                         if (col0 >= 64) {           // attention weights: softmax over each head's 4 points
 #pragma unroll
                             for (int g = 0; g < 8; ++g) {
@@ -505,6 +571,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                                 const float sden = (e0 + e1) + (e2 + e3);
                                 v[g * 4] = e0 / sden; v[g * 4 + 1] = e1 / sden; v[g * 4 + 2] = e2 / sden; v[g * 4 + 3] = e3 / sden;
                             }
+                            stage_store_f32(stg, &v[0], recf + 96, kRecW, rows_valid, lane);
+                        } else {                    // 32 sampling points: resolve positions once, here
+                            const int ti = n / ep.W, tj = n - ti * ep.W;
+                            const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
+                            const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
+                            float widx[32], wfx[32], wfy[32];
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                uint32_t wd;
+                                msda_resolve(v[2 * k], v[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wd, wfx[k], wfy[k]);
+                                widx[k] = __uint_as_float(wd);
+                            }
+                            stage_store_f32(stg, widx, recf, kRecW, rows_valid, lane);
+                            stage_store_f32(stg, wfx, recf + 32, kRecW, rows_valid, lane);
+                            stage_store_f32(stg, wfy, recf + 64, kRecW, rows_valid, lane);
                         }
                     } else {
 #pragma unroll
@@ -584,7 +665,7 @@ template <int BN, int NSPLIT, int EPI>
 inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& a2Hi,
                                   const CUtensorMap& a2Lo, const CUtensorMap& bHi, const CUtensorMap& bLo, int M, int K,
                                   int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st) {
-    using C = Cfg<BN, NSPLIT>;
+    using C = Cfg<BN, NSPLIT, EPI>;
     static bool attr_set = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, EPI>;
     if (!attr_set) {
@@ -595,7 +676,7 @@ inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo
     const int n_tiles_n = n_cols_padded / BN;
     const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    kern<<<grid, kThreadsTc, C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
+    kern<<<grid, tc_threads(EPI), C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
     return cudaSuccess;
 }
 

@@ -178,83 +178,61 @@ __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ l
 // ------------------------------------------------------------------------------------------------
 // multi-scale deformable attention gather (1 level, 8 heads x 4 points, head dim 32)
 // ------------------------------------------------------------------------------------------------
-// out[row][n][32m + d] = sum_p a[n,m,p] * bilinear0( V[row][.][32m + d] at (x, y) )
-// with the reference's coordinate chain evaluated op by op in fp32:
-//   ref = (j + .5) / W                  deformable_head_with_time.py:76-84
-//   loc = ref + off / W                 vmmcv/ops/multi_scale_deform_attn.py:329-334
-//   grid = 2 loc - 1                    :121
-//   x = (grid + 1) * (W / 2) - .5       F.grid_sample(align_corners=False) unnormalisation
-// zero padding outside the map.  One warp per token.  Lane = (head-in-group = lane / 8, 4 channels); the warp walks
-// two groups of 4 heads, so every warp-wide float4 load covers four whole 128-byte lines (one per head): the minimum
-// number of L1 wavefronts for this access pattern (16 KB of V per token).
-__device__ __forceinline__ void msda_point(const float* __restrict__ Vr, float offx, float offy, float a, float refx, float refy,
-                                           float fW, float fH, int W, int H, float (&acc)[4]) {
-    float lx = __fadd_rn(refx, __fdiv_rn(offx, fW));
-    float ly = __fadd_rn(refy, __fdiv_rn(offy, fH));
-    float gx = __fadd_rn(__fmul_rn(2.0f, lx), -1.0f);
-    float gy = __fadd_rn(__fmul_rn(2.0f, ly), -1.0f);
-    float x = __fadd_rn(__fmul_rn(__fadd_rn(gx, 1.0f), fW * 0.5f), -0.5f);
-    float y = __fadd_rn(__fmul_rn(__fadd_rn(gy, 1.0f), fH * 0.5f), -0.5f);
-    float xf = floorf(x), yf = floorf(y);
-    float wx1 = x - xf, wy1 = y - yf;
-    float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
-    // guard against NaN / huge offsets before the int conversion
-    int x0 = (xf >= -2.0f && xf <= fW) ? (int)xf : -2;
-    int y0 = (yf >= -2.0f && yf <= fH) ? (int)yf : -2;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int cy = 0; cy < 2; ++cy) {
-        int yy = y0 + cy;
-        if (yy < 0 || yy >= H) continue;
-        float wy = cy ? wy1 : wy0;
-#pragma unroll
-        for (int cx = 0; cx < 2; ++cx) {
-            int xx = x0 + cx;
-            if (xx < 0 || xx >= W) continue;
-            float wgt = wy * (cx ? wx1 : wx0);
-            float4 v = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(yy * W + xx) * kE));
-            s0 = fmaf(wgt, v.x, s0); s1 = fmaf(wgt, v.y, s1); s2 = fmaf(wgt, v.z, s2); s3 = fmaf(wgt, v.w, s3);
-        }
-    }
-    acc[0] = fmaf(a, s0, acc[0]); acc[1] = fmaf(a, s1, acc[1]); acc[2] = fmaf(a, s2, acc[2]); acc[3] = fmaf(a, s3, acc[3]);
-}
-
+// out[row][n][32m + d] = sum_p a[n,m,p] * sum_corners w_c * V[row][corner_c][32m + d]
+// The sampling positions were resolved by the sampling projection's epilogue (msda_resolve, common.cuh): this kernel
+// is loads + FMAs only, no branches.  One warp per token; lane = (head-in-group = lane / 8, 4 channels); the warp walks
+// two groups of 4 heads so that every warp-wide float4 load covers four whole 128-byte lines (one per head).
 __global__ void __launch_bounds__(256)
-k_msda_gather(const float* __restrict__ V, const float* __restrict__ samp, float* __restrict__ out,
-              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int H, int W, int total_tokens) {
+k_msda_gather(const float* __restrict__ V, const uint32_t* __restrict__ rec, float* __restrict__ out,
+              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int W, int total_tokens) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= total_tokens) return;
     int lane = threadIdx.x & 31;
-    int N = H * W;
-    int row = warp / N, n = warp - row * N;
-    int i = n / W, j = n - i * W;
-    const float* sp = samp + (size_t)warp * kSampW;
-    const float fW = (float)W, fH = (float)H;
-    const float refx = __fdiv_rn((float)j + 0.5f, fW);
-    const float refy = __fdiv_rn((float)i + 0.5f, fH);
+    int row = warp / N;
+    const uint32_t* rp = rec + (size_t)warp * kRecW;
 #pragma unroll
     for (int hg = 0; hg < 2; ++hg) {
         const int m = hg * 4 + (lane >> 3);
         const int ch = m * kHeadDim + (lane & 7) * 4;
         const float* Vr = V + (size_t)row * N * kE + ch;
-        const float4 o01 = *reinterpret_cast<const float4*>(sp + m * 8);
-        const float4 o23 = *reinterpret_cast<const float4*>(sp + m * 8 + 4);
-        const float4 aw = *reinterpret_cast<const float4*>(sp + 64 + m * 4);
+        const uint4 wd = *reinterpret_cast<const uint4*>(rp + m * 4);
+        const float4 fx = *reinterpret_cast<const float4*>(rp + 32 + m * 4);
+        const float4 fy = *reinterpret_cast<const float4*>(rp + 64 + m * 4);
+        const float4 aw = *reinterpret_cast<const float4*>(rp + 96 + m * 4);
+        const uint32_t w4[4] = {wd.x, wd.y, wd.z, wd.w};
+        const float fx4[4] = {fx.x, fx.y, fx.z, fx.w}, fy4[4] = {fy.x, fy.y, fy.z, fy.w}, a4[4] = {aw.x, aw.y, aw.z, aw.w};
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        msda_point(Vr, o01.x, o01.y, aw.x, refx, refy, fW, fH, W, H, acc);
-        msda_point(Vr, o01.z, o01.w, aw.y, refx, refy, fW, fH, W, H, acc);
-        msda_point(Vr, o23.x, o23.y, aw.z, refx, refy, fW, fH, W, H, acc);
-        msda_point(Vr, o23.z, o23.w, aw.w, refx, refy, fW, fH, W, H, acc);
+#pragma unroll
+        for (int p = 0; p < kPoints; ++p) {
+            const uint32_t wv = w4[p];
+            const int base = (int)(wv & 0x03FFFFFFu);
+            const int dx = (int)((wv >> 26) & 1u);
+            const int dy = ((wv >> 27) & 1u) ? W : 0;
+            const float wx1 = fx4[p], wy1 = fy4[p], wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+            const float c00 = (wv & (1u << 28)) ? wy0 * wx0 : 0.f;
+            const float c01 = (wv & (1u << 29)) ? wy0 * wx1 : 0.f;
+            const float c10 = (wv & (1u << 30)) ? wy1 * wx0 : 0.f;
+            const float c11 = (wv & (1u << 31)) ? wy1 * wx1 : 0.f;
+            const float4 v00 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)base * kE));
+            const float4 v01 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dx) * kE));
+            const float4 v10 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy) * kE));
+            const float4 v11 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy + dx) * kE));
+            float s0 = c00 * v00.x, s1 = c00 * v00.y, s2 = c00 * v00.z, s3 = c00 * v00.w;
+            s0 = fmaf(c01, v01.x, s0); s1 = fmaf(c01, v01.y, s1); s2 = fmaf(c01, v01.z, s2); s3 = fmaf(c01, v01.w, s3);
+            s0 = fmaf(c10, v10.x, s0); s1 = fmaf(c10, v10.y, s1); s2 = fmaf(c10, v10.z, s2); s3 = fmaf(c10, v10.w, s3);
+            s0 = fmaf(c11, v11.x, s0); s1 = fmaf(c11, v11.y, s1); s2 = fmaf(c11, v11.z, s2); s3 = fmaf(c11, v11.w, s3);
+            acc[0] = fmaf(a4[p], s0, acc[0]); acc[1] = fmaf(a4[p], s1, acc[1]);
+            acc[2] = fmaf(a4[p], s2, acc[2]); acc[3] = fmaf(a4[p], s3, acc[3]);
+        }
         const size_t o = (size_t)warp * kE + ch;
         if (out) *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         if (out_hi) {
-            __half2 h01, h23, l01, l23;
             const float a0 = acc[0] * kSplitScale, a1 = acc[1] * kSplitScale, a2 = acc[2] * kSplitScale, a3 = acc[3] * kSplitScale;
-            h01 = __floats2half2_rn(a0, a1); h23 = __floats2half2_rn(a2, a3);
+            __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
             *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
             if (out_lo) {
                 const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-                l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y); l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+                __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y), l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
                 *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
             }
         }
