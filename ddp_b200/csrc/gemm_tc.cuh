@@ -550,43 +550,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                             v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, c4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, c4.w);
                         }
                     } else if (EPI == EPI_SAMPLING) {
-                        // columns 0..63 offsets (half 0), 64..95 attention logits, 96..127 padding (half 1)
+                        // accumulator columns: 0..63 = (x, y) offsets of 32 sampling points, 64..95 attention logits, 96..127 padding.
+                        // Any warp of a lane quarter may read any column, so the two warps of a quarter split the points:
+                        // warp `half` resolves points 16*half .. 16*half+15 (columns 32*half .. +31); half 1 also owns the
+                        // attention weights.  (v[] was loaded from columns cbeg.. = 64*half..; reload what this warp needs.)
                         const int n = (int)(srow % ep.N_tok);
-                        const float* pp = ep.pew + (size_t)n * kSampW + col0;
-                        const int nvalid = col0 < 64 ? 64 : 32;
-#pragma unroll
-                        for (int i = 0; i < W / 4; ++i) {
-                            if (i * 4 < nvalid) {
-                                const float4 p4 = *reinterpret_cast<const float4*>(pp + i * 4);
-                                v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, p4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, p4.y);
-                                v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, p4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, p4.w);
-                            }
-                        }
                         float* recf = reinterpret_cast<float*>(ep.rec + (size_t)wrow0 * kRecW);
-                        if (col0 >= 64) {           // attention weights: softmax over each head's 4 points
+                        const float* pp = ep.pew + (size_t)n * kSampW;
+                        float o[32];
+                        tmem_ld32(t_row + 32 * half, o);
 #pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float mx = fmaxf(fmaxf(v[g * 4], v[g * 4 + 1]), fmaxf(v[g * 4 + 2], v[g * 4 + 3]));
-                                const float e0 = expf(v[g * 4] - mx), e1 = expf(v[g * 4 + 1] - mx), e2 = expf(v[g * 4 + 2] - mx), e3 = expf(v[g * 4 + 3] - mx);
-                                const float sden = (e0 + e1) + (e2 + e3);
-                                v[g * 4] = e0 / sden; v[g * 4 + 1] = e1 / sden; v[g * 4 + 2] = e2 / sden; v[g * 4 + 3] = e3 / sden;
-                            }
-                            stage_store_f32(stg, &v[0], recf + 96, kRecW, rows_valid, lane);
-                        } else {                    // 32 sampling points: resolve positions once, here
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 p4 = *reinterpret_cast<const float4*>(pp + 32 * half + i * 4);
+                            o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
+                            o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
+                        }
+                        if (ep.out) stage_store_f32(stg, o, ep.out + (size_t)wrow0 * ep.ldc + 32 * half, ep.ldc, rows_valid, lane);
+                        {
                             const int ti = n / ep.W, tj = n - ti * ep.W;
                             const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
                             const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
-                            float widx[32], wfx[32], wfy[32];
+                            uint4 widx[4], wfx[4], wfy[4];
+                            uint32_t* wi = reinterpret_cast<uint32_t*>(widx);
+                            float* fxp = reinterpret_cast<float*>(wfx);
+                            float* fyp = reinterpret_cast<float*>(wfy);
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                uint32_t wd;
-                                msda_resolve(v[2 * k], v[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wd, wfx[k], wfy[k]);
-                                widx[k] = __uint_as_float(wd);
-                            }
-                            stage_store_f32(stg, widx, recf, kRecW, rows_valid, lane);
-                            stage_store_f32(stg, wfx, recf + 32, kRecW, rows_valid, lane);
-                            stage_store_f32(stg, wfy, recf + 64, kRecW, rows_valid, lane);
+                            for (int k = 0; k < 16; ++k)
+                                msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
+                            // 16 words = 64-byte rows: same tile geometry as 32 fp16 columns
+                            __half* rech = reinterpret_cast<__half*>(recf);
+                            stage_store_f16_32(stg, widx, rech + 2 * (16 * half), 2 * kRecW, rows_valid, lane);
+                            stage_store_f16_32(stg, wfx, rech + 2 * (32 + 16 * half), 2 * kRecW, rows_valid, lane);
+                            stage_store_f16_32(stg, wfy, rech + 2 * (64 + 16 * half), 2 * kRecW, rows_valid, lane);
                         }
+                        if (half == 1) {            // attention weights: softmax over each head's 4 points (columns 64..95)
+                            float a[32];
+                            tmem_ld32(t_row + 64, a);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + i * 4);
+                                a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
+                                a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 8; ++g) {
+                                const float mx = fmaxf(fmaxf(a[g * 4], a[g * 4 + 1]), fmaxf(a[g * 4 + 2], a[g * 4 + 3]));
+                                const float e0 = expf(a[g * 4] - mx), e1 = expf(a[g * 4 + 1] - mx), e2 = expf(a[g * 4 + 2] - mx), e3 = expf(a[g * 4 + 3] - mx);
+                                const float sden = (e0 + e1) + (e2 + e3);
+                                a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
+                            }
+                            stage_store_f32(stg, a, recf + 96, kRecW, rows_valid, lane);
+                            if (ep.out) stage_store_f32(stg, a, ep.out + (size_t)wrow0 * ep.ldc + 64, ep.ldc, rows_valid, lane);
+                        }
+                        continue;       // everything stored above
                     } else {
 #pragma unroll
                         for (int i = 0; i < W / 4; ++i) {

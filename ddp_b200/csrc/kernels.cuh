@@ -182,7 +182,7 @@ __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ l
 // The sampling positions were resolved by the sampling projection's epilogue (msda_resolve, common.cuh): this kernel
 // is loads + FMAs only, no branches.  One warp per token; lane = (head-in-group = lane / 8, 4 channels); the warp walks
 // two groups of 4 heads so that every warp-wide float4 load covers four whole 128-byte lines (one per head).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_msda_gather(const float* __restrict__ V, const uint32_t* __restrict__ rec, float* __restrict__ out,
               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int W, int total_tokens) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -202,21 +202,28 @@ k_msda_gather(const float* __restrict__ V, const uint32_t* __restrict__ rec, flo
         const uint32_t w4[4] = {wd.x, wd.y, wd.z, wd.w};
         const float fx4[4] = {fx.x, fx.y, fx.z, fx.w}, fy4[4] = {fy.x, fy.y, fy.z, fy.w}, a4[4] = {aw.x, aw.y, aw.z, aw.w};
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // all 16 corner loads of this head group are issued before any is used (memory-level parallelism)
+        float4 vv[kPoints][4];
 #pragma unroll
         for (int p = 0; p < kPoints; ++p) {
             const uint32_t wv = w4[p];
             const int base = (int)(wv & 0x03FFFFFFu);
             const int dx = (int)((wv >> 26) & 1u);
             const int dy = ((wv >> 27) & 1u) ? W : 0;
+            vv[p][0] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)base * kE));
+            vv[p][1] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dx) * kE));
+            vv[p][2] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy) * kE));
+            vv[p][3] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy + dx) * kE));
+        }
+#pragma unroll
+        for (int p = 0; p < kPoints; ++p) {
+            const uint32_t wv = w4[p];
             const float wx1 = fx4[p], wy1 = fy4[p], wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
             const float c00 = (wv & (1u << 28)) ? wy0 * wx0 : 0.f;
             const float c01 = (wv & (1u << 29)) ? wy0 * wx1 : 0.f;
             const float c10 = (wv & (1u << 30)) ? wy1 * wx0 : 0.f;
             const float c11 = (wv & (1u << 31)) ? wy1 * wx1 : 0.f;
-            const float4 v00 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)base * kE));
-            const float4 v01 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dx) * kE));
-            const float4 v10 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy) * kE));
-            const float4 v11 = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy + dx) * kE));
+            const float4 v00 = vv[p][0], v01 = vv[p][1], v10 = vv[p][2], v11 = vv[p][3];
             float s0 = c00 * v00.x, s1 = c00 * v00.y, s2 = c00 * v00.z, s3 = c00 * v00.w;
             s0 = fmaf(c01, v01.x, s0); s1 = fmaf(c01, v01.y, s1); s2 = fmaf(c01, v01.z, s2); s3 = fmaf(c01, v01.w, s3);
             s0 = fmaf(c10, v10.x, s0); s1 = fmaf(c10, v10.y, s1); s2 = fmaf(c10, v10.z, s2); s3 = fmaf(c10, v10.w, s3);
