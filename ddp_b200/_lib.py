@@ -24,7 +24,7 @@ EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "dd
            "ddp_get_schedule", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
            "ddp_profile_collect", "ddp_kernel_class_name"]
-K_COUNT = 12
+K_COUNT = 13
 
 
 class DDPConfig(ctypes.Structure):

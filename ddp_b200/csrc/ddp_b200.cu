@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "ffn_fused.cuh"
 #include "kernels.cuh"
 
 using namespace ddp;
@@ -38,6 +39,7 @@ struct LayerW {
 struct TcWeight {
     __half *hi = nullptr, *lo = nullptr;
     CUtensorMap map_hi, map_lo;
+    CUtensorMap map_alt_hi, map_alt_lo;      // second box shape for the fused FFN kernel (W1: 64 rows, W2: 128 rows)
     float inv_scale = 1.f;      // 1 / (2^shift * activation scale): multiplies the accumulator
     int rows_pad = 0, K = 0, bn = 0;
 };
@@ -67,6 +69,8 @@ struct ddp_handle {
 
     // tcgen05 path (gemm_mode != FP32)
     bool tc = false;
+    bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
+    unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
     int nsplit = 1;
     int num_sms = 148;
     __half* tc_arena = nullptr;
@@ -407,6 +411,9 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
         if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st, kE))) return rc;
         if ((rc = make_tc_weight(h, T.f1, cur, kFFN, kE, 256, {{w1->dev, &w1->host, kFFN, kE, 1, 0, 0}}, st))) return rc;
         if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st, kE))) return rc;
+        if (!tc::make_map_f16(&T.f1.map_alt_hi, T.f1.hi, kFFN, kE, 64) || !tc::make_map_f16(&T.f1.map_alt_lo, T.f1.lo, kFFN, kE, 64) ||
+            !tc::make_map_f16(&T.f2.map_alt_hi, T.f2.hi, kE, kFFN + kE, 128) || !tc::make_map_f16(&T.f2.map_alt_lo, T.f2.lo, kE, kFFN + kE, 128))
+            return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fused-FFN weight maps");
     }
     if (seg) {
         WeightSpec* w = spec("decode_head.conv_seg.weight");
@@ -544,6 +551,12 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
     h->tc = cfg->gemm_mode != DDP_GEMM_FP32;
     h->nsplit = cfg->gemm_mode == DDP_GEMM_TC_3XF16 ? 3 : 1;
     h->num_sms = prop.multiProcessorCount;
+    {
+        const char* e = getenv("DDP_B200_FUSE_FFN");
+        h->fuse_ffn = h->tc && (e == nullptr || atoi(e) != 0);
+        const char* d = getenv("DDP_B200_FFN_DBG");
+        if (d && atoi(d) != 0 && cudaMalloc(&h->ffn_dbg, 64) == cudaSuccess) cudaMemset(h->ffn_dbg, 0, 64);
+    }
     if (h->tc && !tc::get_encode_fn()) {
         delete h;
         return fail(nullptr, DDP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -767,7 +780,17 @@ int ddp_clear_debug(ddp_handle* h) {
     return DDP_OK;
 }
 
-int64_t ddp_last_launch_count(const ddp_handle* h) { return h ? h->launches : 0; }
+int64_t ddp_last_launch_count(const ddp_handle* h) {
+    if (h && h->ffn_dbg) {          // profiling aid: dump and reset the MMA-issuer cycle counters
+        unsigned long long v[8];
+        if (cudaMemcpy(v, h->ffn_dbg, 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            fprintf(stderr, "[ffn_fused issuer cycles] total %llu ring_wait %llu d1_empty %llu a2_full %llu d2_empty %llu a1_full %llu\n",
+                    v[0], v[1], v[2], v[3], v[4], v[5]);
+            cudaMemset(h->ffn_dbg, 0, 64);
+        }
+    }
+    return h ? h->launches : 0;
+}
 
 static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half* state_hi, __half* state_lo,
                       cudaStream_t st) {
@@ -873,6 +896,22 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                     TC_GEMM2(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
                 }
                 if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+                if (h->fuse_ffn) {   // q = FiLM(LN2(q + W2 gelu(W1 q + b1) + b2)) in ONE kernel, hidden activation kept in TMEM
+                    tc::FfnParams fp{};
+                    fp.s1_16 = T.f1.inv_scale * tc::kActScale; fp.s2 = T.f2.inv_scale; fp.b1 = L.b1; fp.b2 = L.b2;
+                    fp.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; fp.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
+                    fp.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                    fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
+                    fp.dbg = h->ffn_dbg;
+                    prof_begin(h, DDP_K_FFN_FUSED, st);
+                    cudaError_t e_ = s3 ? tc::launch_ffn_fused<3>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
+                                                                  T.f2.map_alt_lo, M, fp, h->num_sms, st)
+                                        : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
+                                                                  T.f2.map_alt_hi, M, fp, h->num_sms, st);
+                    prof_end(h, st);
+                    if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
+                    LAUNCH_CHECK(h);
+                } else {
                 {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
                     tc::EpiParams ep{};
                     ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
@@ -885,6 +924,7 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                     ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                     ep.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; ep.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
                     TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
+                }
                 }
             } else {
             {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
@@ -996,7 +1036,8 @@ int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_
 
 const char* ddp_kernel_class_name(int cls) {
     static const char* names[DDP_K_COUNT] = {"cond", "head_in", "value_proj", "sampling_proj", "msda_gather", "out_proj_ln",
-                                             "ffn1_gelu", "ffn2_ln_film", "head_out", "step_update", "finalize", "layout"};
+                                             "ffn1_gelu", "ffn2_ln_film", "head_out", "step_update", "finalize", "layout",
+                                             "ffn_fused"};
     return (cls >= 0 && cls < DDP_K_COUNT) ? names[cls] : nullptr;
 }
 

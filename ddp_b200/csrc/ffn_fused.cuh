@@ -1,0 +1,480 @@
+// Fused FFN block for sm_100a:  q <- FiLM(LN2(q + W2 gelu(W1 q + b1) + b2))   for a 128-token tile per CTA,
+// with the 1024-wide hidden activation never leaving the SM (the unfused pair writes + reads 8 KB/token of it).
+//
+//   A1 = q planes (128 x 256, fp16 hi/lo)        shared memory, loaded once per tile by TMA
+//   for each chunk c of 64 hidden columns (16 chunks):
+//       D1 (TMEM, 128 x 64 fp32)  = A1 * W1[c]^T                       tcgen05.mma, A and B from shared memory
+//       hid = gelu(D1 * s + b1)  -> fp16 hi/lo planes written back into TMEM (tcgen05.st, 2 halves per column)
+//       D2 (TMEM, 128 x 256 fp32) += hid * W2[:, c]^T                  tcgen05.mma with the A operand FROM TMEM
+//   D2 += A1 * (2^shift I)^T        (the residual, through the identity block of the augmented W2)
+//   epilogue: LayerNorm + folded FiLM, fp16 planes (and optionally fp32) of the new q
+//
+// TMEM (512 columns): D2 [0,256) | D1 x2 [256,384) | hid planes x2 [384,512) (hi 32 + lo 32 columns per buffer).
+// Warps: 0 TMA producer (A1 + a 4-stage ring of 16 KB weight units), 1 MMA issuer, 2..17 epilogue (thread = row,
+// four warps per TMEM lane quarter).  MMA1 of chunk c overlaps the GELU epilogue of chunk c-1 and MMA2 of chunk c-1.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace ddp {
+namespace tc {
+
+struct FfnParams {
+    float s1_16;             // 16 / (2^shift1 * 16): turns the D1 accumulator into 16 * (W1 q)
+    float s2;                // 1 / (2^shift2 * 16)
+    const float* b1;         // [1024]
+    const float* b2;         // [256]
+    const float* ln_g;       // [256] LN2 gamma * (film scale + 1)
+    const float* ln_b;       // [256] LN2 beta * (film scale + 1) + film shift
+    SplitOut split;          // planes of the new q
+    float* out;              // optional fp32 copy [M][256]
+    unsigned long long* dbg; // optional [8] cycle counters of the MMA issuer (profiling aid)
+};
+
+constexpr int kFfnThreads = 32 * 18;
+constexpr int kFfnUnit = 16384;
+constexpr int kFfnRing = 4;
+constexpr int kFfnSmem = 8 * kFfnUnit + kFfnRing * kFfnUnit + kStageAreaBytes + 1024 + 256;
+static_assert(kFfnSmem <= 232448, "fused FFN kernel exceeds shared memory");
+
+// tcgen05.mma with the A operand in tensor memory (lane = row, two fp16 K-elements per 32-bit column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : TMEM_R16(r, 0)
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kFfnThreads, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_constant__ CUtensorMap mapA1lo,
+                 const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ CUtensorMap mapW1lo,
+                 const __grid_constant__ CUtensorMap mapW2hi, const __grid_constant__ CUtensorMap mapW2lo,
+                 int M, FfnParams p) {
+    constexpr int kChunks = kFFN / 64;                  // 16
+    constexpr int kPl = NSPLIT > 1 ? 2 : 1;             // planes per operand
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* a1 = smem;                                  // [plane][kb] 16 KB tiles
+    uint8_t* ring = smem + 8 * kFfnUnit;
+    uint8_t* stage_tiles = ring + kFfnRing * kFfnUnit;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + kStageAreaBytes);
+    uint64_t* a1_full = bars + 0;
+    uint64_t* a1_empty = bars + 1;
+    uint64_t* ring_full = bars + 2;                      // [4]
+    uint64_t* ring_empty = bars + 6;                     // [4]
+    uint64_t* d1_full = bars + 10;                       // [2]
+    uint64_t* d1_empty = bars + 12;                      // [2]
+    uint64_t* a2_full = bars + 14;                       // [2]
+    uint64_t* a2_empty = bars + 16;                      // [2]
+    uint64_t* d2_full = bars + 18;
+    uint64_t* d2_empty = bars + 19;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (M + BM - 1) / BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA1hi); tma_prefetch_desc(&mapW1hi); tma_prefetch_desc(&mapW2hi);
+        if (NSPLIT > 1) { tma_prefetch_desc(&mapA1lo); tma_prefetch_desc(&mapW1lo); tma_prefetch_desc(&mapW2lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a1_full, 1); mbar_init(a1_empty, 1);
+        for (int s = 0; s < kFfnRing; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], 16);
+            mbar_init(&a2_full[b], 16); mbar_init(&a2_empty[b], 1);
+        }
+        mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tD2 = tmem_base, tD1 = tmem_base + 256, tA2 = tmem_base + 384;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t rphase = 0; uint32_t tphase = 0;
+            auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int bytes_each, int c0, int c1) {
+                // one ring unit: hi tile at the stage base, optional lo tile right behind it
+                mbar_wait(&ring_empty[stage], rphase ^ 1);
+                uint8_t* st = ring + stage * kFfnUnit;
+                mbar_expect_tx(&ring_full[stage], lo ? 2 * bytes_each : bytes_each);
+                tma_load_2d(st, hi, &ring_full[stage], c0, c1);
+                if (lo) tma_load_2d(st + bytes_each, lo, &ring_full[stage], c0, c1);
+                if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
+            };
+            auto put_w2 = [&](int cc) {       // W2 columns of hidden chunk cc: (nh0: hi, lo), (nh1: hi, lo)
+                for (int nh = 0; nh < 2; ++nh) {
+                    put(&mapW2hi, nullptr, kFfnUnit, cc * 64, nh * 128);
+                    if (NSPLIT > 1) put(&mapW2lo, nullptr, kFfnUnit, cc * 64, nh * 128);
+                }
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = tile * BM;
+                mbar_wait(a1_empty, tphase ^ 1);
+                mbar_expect_tx(a1_full, kPl * 4 * kFfnUnit);
+                for (int kb = 0; kb < 4; ++kb) {
+                    tma_load_2d(a1 + kb * kFfnUnit, &mapA1hi, a1_full, kb * BK, m0);
+                    if (NSPLIT > 1) tma_load_2d(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
+                }
+                for (int c = 0; c < kChunks; ++c) {
+                    for (int kb = 0; kb < 4; ++kb)       // W1 rows of hidden chunk c, K block kb: hi 8 KB | lo 8 KB
+                        put(&mapW1hi, NSPLIT > 1 ? &mapW1lo : nullptr, kFfnUnit / 2, kb * BK, c * 64);
+                    if (c >= 1) put_w2(c - 1);
+                }
+                put_w2(kChunks - 1);
+                for (int kb = 0; kb < 4; ++kb)           // identity block of the augmented W2 (hi plane only)
+                    for (int nh = 0; nh < 2; ++nh) put(&mapW2hi, nullptr, kFfnUnit, kFFN + kb * BK, nh * 128);
+                tphase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp runs the loop; tcgen05 instructions on the elected lane) =====================
+        {
+            constexpr uint32_t idesc64 = make_idesc(BM, 64);
+            constexpr uint32_t idesc128 = make_idesc(BM, 128);
+            int stage = 0; uint32_t rphase = 0, tphase = 0;
+            uint32_t d1e_phase[2] = {0, 0}, a2f_phase[2] = {0, 0};
+            uint32_t d2e_phase = 0;
+            const uint32_t a1_addr = smem_u32(a1);
+            long long tw_ring = 0, tw_d1e = 0, tw_a2f = 0, tw_d2e = 0, tw_a1 = 0, t_all = clock64();
+            auto ring_wait = [&]() -> uint32_t {
+                long long t0 = clock64();
+                mbar_wait(&ring_full[stage], rphase);
+                tc_fence_after();
+                tw_ring += clock64() - t0;
+                return smem_u32(ring + stage * kFfnUnit);
+            };
+            auto ring_release = [&]() {
+                if (elect_one()) umma_commit(&ring_empty[stage]);
+                __syncwarp();
+                if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
+            };
+            auto mma2 = [&](int cc) {                    // D2 += hid(cc) * W2[:, cc]^T, hid planes in TMEM buffer cc & 1
+                const int b = cc & 1;
+                { long long t0 = clock64(); mbar_wait(&a2_full[b], a2f_phase[b]); a2f_phase[b] ^= 1; tw_a2f += clock64() - t0; }
+                tc_fence_after();
+                const uint32_t ahi = tA2 + 64 * b, alo = ahi + 32;
+                for (int nh = 0; nh < 2; ++nh) {
+                    const uint32_t uhi = ring_wait();
+                    const uint64_t bhi = make_smem_desc(uhi);
+                    const uint32_t d = tD2 + nh * 128;
+                    if (NSPLIT > 1) {
+                        // the lo unit sits in the next ring stage: peek it without releasing the hi unit
+                        int s2 = stage + 1; uint32_t ph2 = rphase;
+                        if (s2 == kFfnRing) { s2 = 0; ph2 ^= 1; }
+                        mbar_wait(&ring_full[s2], ph2);
+                        tc_fence_after();
+                        const uint64_t blo = make_smem_desc(smem_u32(ring + s2 * kFfnUnit));
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t acc = (cc | k) != 0;
+                                umma_f16_ts(d, alo + 8 * k, bhi + 2 * k, idesc128, acc);
+                                umma_f16_ts(d, ahi + 8 * k, blo + 2 * k, idesc128, 1u);
+                                umma_f16_ts(d, ahi + 8 * k, bhi + 2 * k, idesc128, 1u);
+                            }
+                        }
+                        __syncwarp();
+                        ring_release();
+                        ring_release();
+                    } else {
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_ts(d, ahi + 8 * k, bhi + 2 * k, idesc128, (cc | k) != 0);
+                        }
+                        __syncwarp();
+                        ring_release();
+                    }
+                }
+                if (elect_one()) umma_commit(&a2_empty[b]);
+                __syncwarp();
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                { long long t0 = clock64(); mbar_wait(a1_full, tphase); tw_a1 += clock64() - t0; }
+                tc_fence_after();
+                for (int c = 0; c <= kChunks; ++c) {
+                    if (c < kChunks) {                   // D1[c & 1] = A1 * W1[c]^T
+                        const int b = c & 1;
+                        { long long t0 = clock64(); mbar_wait(&d1_empty[b], d1e_phase[b] ^ 1); d1e_phase[b] ^= 1; tw_d1e += clock64() - t0; }
+                        tc_fence_after();
+                        const uint32_t d = tD1 + 64 * b;
+                        for (int kb = 0; kb < 4; ++kb) {
+                            const uint32_t u = ring_wait();
+                            const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
+                            const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
+                            const uint64_t bhi = make_smem_desc(u), blo = make_smem_desc(u + kFfnUnit / 2);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t acc = (kb | k) != 0;
+                                    if (NSPLIT > 1) {
+                                        umma_f16(d, alo + 2 * k, bhi + 2 * k, idesc64, acc);
+                                        umma_f16(d, ahi + 2 * k, blo + 2 * k, idesc64, 1u);
+                                        umma_f16(d, ahi + 2 * k, bhi + 2 * k, idesc64, 1u);
+                                    } else {
+                                        umma_f16(d, ahi + 2 * k, bhi + 2 * k, idesc64, acc);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                            ring_release();
+                        }
+                        if (elect_one()) umma_commit(&d1_full[b]);
+                        __syncwarp();
+                    }
+                    if (c >= 1) {
+                        if (c == 1) {                    // D2 of the previous tile must have been drained
+                            { long long t0 = clock64(); mbar_wait(d2_empty, d2e_phase ^ 1); d2e_phase ^= 1; tw_d2e += clock64() - t0; }
+                            tc_fence_after();
+                        }
+                        mma2(c - 1);
+                    }
+                }
+                // residual: D2 += q * (2^shift I)^T with q's planes still in shared memory
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
+                    const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
+                    for (int nh = 0; nh < 2; ++nh) {
+                        const uint64_t bi = make_smem_desc(ring_wait());
+                        const uint32_t d = tD2 + nh * 128;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (NSPLIT > 1) umma_f16(d, alo + 2 * k, bi + 2 * k, idesc128, 1u);
+                                umma_f16(d, ahi + 2 * k, bi + 2 * k, idesc128, 1u);
+                            }
+                        }
+                        __syncwarp();
+                        ring_release();
+                    }
+                }
+                if (elect_one()) {
+                    umma_commit(a1_empty);               // q planes may be overwritten by the next tile's load
+                    umma_commit(d2_full);
+                }
+                __syncwarp();
+                tphase ^= 1;
+            }
+            if (p.dbg && lane == 0) {
+                atomicAdd(&p.dbg[0], (unsigned long long)(clock64() - t_all));
+                atomicAdd(&p.dbg[1], (unsigned long long)tw_ring);
+                atomicAdd(&p.dbg[2], (unsigned long long)tw_d1e);
+                atomicAdd(&p.dbg[3], (unsigned long long)tw_a2f);
+                atomicAdd(&p.dbg[4], (unsigned long long)tw_d2e);
+                atomicAdd(&p.dbg[5], (unsigned long long)tw_a1);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps 2..17: thread = row =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;
+        const int part = ew >> 2;                        // which quarter of the columns
+        float* stg = reinterpret_cast<float*>(stage_tiles + ew * 2048);
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        uint32_t d1f_phase[2] = {0, 0}, a2e_phase[2] = {0, 0};
+        uint32_t d2f_phase = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int m0 = tile * BM;
+            const int wrow0 = m0 + q * 32;
+            const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
+            // ---- per hidden chunk: GELU of this warp's 16 columns, planes back into TMEM ----
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                const int b = c & 1;
+                mbar_wait(&d1_full[b], d1f_phase[b]); d1f_phase[b] ^= 1;
+                tc_fence_after();
+                float v[16];
+                tmem_ld16(tD1 + 64 * b + part * 16 + lane_sel, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d1_empty[b]);            // D1[b] may be overwritten by MMA1 of chunk c + 2
+                uint32_t hi[8], lo[8];
+                const float* bp = p.b1 + c * 64 + part * 16;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i * 4));
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                    float g[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float z16 = fmaf(v[i * 4 + e], p.s1_16, bb[e] * kActScale);
+                        const float u = fabsf(z16) * (0.70710678118654752440f * kInvActScale);
+                        float t, ex;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+                        float pl = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+                        pl = fmaf(pl, t, 0.5f * 1.421413741f);
+                        pl = fmaf(pl, t, 0.5f * -0.284496736f);
+                        pl = fmaf(pl, t, 0.5f * 0.254829592f);
+                        pl *= t;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u * u * -1.44269504088896340736f));
+                        const float hh = pl * ex;
+                        g[e] = z16 * (z16 < 0.f ? hh : 1.0f - hh);
+                    }
+                    const __half2 h01 = __floats2half2_rn(g[0], g[1]), h23 = __floats2half2_rn(g[2], g[3]);
+                    hi[i * 2] = *reinterpret_cast<const uint32_t*>(&h01);
+                    hi[i * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+                    if (NSPLIT > 1) {
+                        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(g[0] - b01.x, g[1] - b01.y);
+                        const __half2 l23 = __floats2half2_rn(g[2] - b23.x, g[3] - b23.y);
+                        lo[i * 2] = *reinterpret_cast<const uint32_t*>(&l01);
+                        lo[i * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+                    }
+                }
+                // hid planes buffer b must have been consumed by MMA2 of chunk c - 2
+                mbar_wait(&a2_empty[b], a2e_phase[b] ^ 1); a2e_phase[b] ^= 1;
+                tc_fence_after();
+                tmem_st8(tA2 + 64 * b + part * 8 + lane_sel, hi);
+                if (NSPLIT > 1) tmem_st8(tA2 + 64 * b + 32 + part * 8 + lane_sel, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a2_full[b]);
+            }
+            // ---- final: LayerNorm (+ folded FiLM) of this warp's 64 columns of D2 ----
+            mbar_wait(d2_full, d2f_phase); d2f_phase ^= 1;
+            tc_fence_after();
+            const uint32_t t_row = tD2 + part * 64 + lane_sel;
+            float mean = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                float v[32];
+                tmem_ld32(t_row + c, v);
+                float cs = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + part * 64 + c + i * 4));
+                    v[i * 4 + 0] = fmaf(v[i * 4 + 0], p.s2, b4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], p.s2, b4.y);
+                    v[i * 4 + 2] = fmaf(v[i * 4 + 2], p.s2, b4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], p.s2, b4.w);
+                    cs += (v[i * 4 + 0] + v[i * 4 + 1]) + (v[i * 4 + 2] + v[i * 4 + 3]);
+                }
+                tmem_st32(t_row + c, v);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                const float cm = cs * (1.0f / 32.0f);
+                float cm2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { const float d = v[i] - cm; cm2 = fmaf(d, d, cm2); }
+                const float na = (float)c, nb = 32.0f, nab = na + nb;
+                const float delta = cm - mean;
+                mean += delta * (nb / nab);
+                m2 += cm2 + delta * delta * (na * nb / nab);
+            }
+            {   // combine the four column quarters of each row: every warp of the lane quarter gets all four partials
+                for (int w = 0; w < 4; ++w) {
+                    float2* dst = reinterpret_cast<float2*>(stage_tiles + (w * 4 + (ew & 3)) * 2048);
+                    dst[part * 32 + lane] = make_float2(mean, m2);
+                }
+                named_bar_sync(1 + q, 128);
+                const float2* mine = reinterpret_cast<const float2*>(stg);
+                float mu = 0.f, s2v = 0.f, n = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {            // fixed order: identical result in all four warps
+                    const float2 o = mine[w * 32 + lane];
+                    const float nb = 64.0f, nab = n + nb;
+                    const float delta = o.x - mu;
+                    mu += delta * (nb / nab);
+                    s2v += o.y + delta * delta * (n * nb / nab);
+                    n = nab;
+                }
+                mean = mu; m2 = s2v;
+                __syncwarp();
+            }
+            const float rstd = 1.0f / sqrtf(m2 * (1.0f / kE) + 1e-5f);
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                float v[32];
+                tmem_ld32(t_row + c, v);
+                const int col = part * 64 + c;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + col + i * 4));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + i * 4));
+                    v[i * 4 + 0] = fmaf((v[i * 4 + 0] - mean) * rstd, g4.x, b4.x);
+                    v[i * 4 + 1] = fmaf((v[i * 4 + 1] - mean) * rstd, g4.y, b4.y);
+                    v[i * 4 + 2] = fmaf((v[i * 4 + 2] - mean) * rstd, g4.z, b4.z);
+                    v[i * 4 + 3] = fmaf((v[i * 4 + 3] - mean) * rstd, g4.w, b4.w);
+                }
+                uint4 hi[4], lo[4];
+                __half2* h2 = reinterpret_cast<__half2*>(hi);
+                __half2* l2 = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float a = v[2 * i] * kActScale, bq = v[2 * i + 1] * kActScale;
+                    const __half2 hh = __floats2half2_rn(a, bq);
+                    h2[i] = hh;
+                    if (NSPLIT > 1) {
+                        const float2 back = __half22float2(hh);
+                        l2[i] = __floats2half2_rn(a - back.x, bq - back.y);
+                    }
+                }
+                stage_store_f16_32(stg, hi, p.split.hi + (size_t)wrow0 * p.split.ld + col, p.split.ld, rows_valid, lane);
+                if (NSPLIT > 1)
+                    stage_store_f16_32(stg, lo, p.split.lo + (size_t)wrow0 * p.split.ld + col, p.split.ld, rows_valid, lane);
+                if (p.out) {                             // fp32 copy for test taps: 16 columns (64-byte rows) at a time
+                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[0]),
+                                       reinterpret_cast<__half*>(p.out + (size_t)wrow0 * kE + col), 2 * kE, rows_valid, lane);
+                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[16]),
+                                       reinterpret_cast<__half*>(p.out + (size_t)wrow0 * kE + col + 16), 2 * kE, rows_valid, lane);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty);
+            named_bar_sync(1 + q, 128);                  // partners may reuse this warp's tile for the next tile's partials
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int NSPLIT>
+inline cudaError_t launch_ffn_fused(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
+                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
+                                    const FfnParams& p, int num_sms, cudaStream_t st) {
+    static bool attr_set = false;
+    auto kern = ffn_fused_kernel<NSPLIT>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int n_tiles = (M + BM - 1) / BM;
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    kern<<<grid, kFfnThreads, kFfnSmem, st>>>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
+    return cudaSuccess;
+}
+
+}  // namespace tc
+}  // namespace ddp

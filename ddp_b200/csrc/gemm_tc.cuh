@@ -86,6 +86,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+// One lane of a converged warp (elect.sync picks the same lane every time).  The MMA-issuing WARP runs its loop
+// with all 32 lanes (warp-uniform control flow and operands, so descriptors live in uniform registers) and only
+// the tcgen05 instructions themselves are predicated on the elected lane.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T ; one thread issues for the CTA
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -366,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -386,16 +395,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);       // +32 B per K=16 step inside the swizzle atom
                         const uint32_t accum = (kb | k) != 0;
-                        if (NSPLIT > 1) {
-                            umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, accum);    // small terms first
-                            umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
-                        } else {
-                            umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, accum);
+                        if (elect_one()) {
+                            if (NSPLIT > 1) {
+                                umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, accum);    // small terms first
+                                umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                                umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, accum);
+                            }
                         }
                     }
-                    umma_commit(&empty_bar[stage]);                 // stage free once these MMAs retire
-                    if (kb == n_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+                    if (elect_one()) {
+                        umma_commit(&empty_bar[stage]);                 // stage free once these MMAs retire
+                        if (kb == n_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+                    }
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
