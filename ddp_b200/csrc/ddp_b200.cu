@@ -86,6 +86,7 @@ struct ddp_handle {
     float *pe = nullptr, *pew[kMaxLayers] = {nullptr};
     float *d_time_in = nullptr, *four = nullptr, *h1 = nullptr, *temb = nullptr, *film = nullptr;
     float *film_g = nullptr, *film_b = nullptr;     // LN2 gamma/beta with the FiLM (scale+1, shift) folded in, per (step, layer)
+    float *film_one = nullptr, *fg_one = nullptr, *fb_one = nullptr;   // the same for one caller-given embedding (ddp_head_forward)
     size_t ws_bytes = 0, ws_compute_bytes = 0;
 
     // schedule (host)
@@ -730,6 +731,7 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     for (int j = 0; j < Lc; ++j) need((size_t)N * kSampW);
     need(T); need((size_t)T * 32); need((size_t)T * kTimeDim); need((size_t)T * kTimeDim); need((size_t)T * Lc * 2 * kE);
     need((size_t)T * Lc * kE); need((size_t)T * Lc * kE);
+    need((size_t)Lc * 2 * kE); need((size_t)Lc * kE); need((size_t)Lc * kE);
     CUDA_TRY(h, cudaMalloc(&h->p_arena, fl * sizeof(float)));
     Bump b(h->p_arena);
     h->pe = b.take((size_t)N * kE);
@@ -739,6 +741,9 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     h->film = b.take((size_t)T * Lc * 2 * kE);
     h->film_g = b.take((size_t)T * Lc * kE);
     h->film_b = b.take((size_t)T * Lc * kE);
+    h->film_one = b.take((size_t)Lc * 2 * kE);
+    h->fg_one = b.take((size_t)Lc * kE);
+    h->fb_one = b.take((size_t)Lc * kE);
     cudaStream_t st = 0;
     k_sine_pe<<<(N * kE + 255) / 256, 256, 0, st>>>(h->pe, height, width);
     LAUNCH_CHECK(h);
@@ -790,6 +795,137 @@ int64_t ddp_last_launch_count(const ddp_handle* h) {
         }
     }
     return h ? h->launches : 0;
+}
+
+// One evaluation of the time-conditioned denoiser on the tokens in ws.q (+ planes): 6 x (MSDA, LN, FFN, LN, FiLM) and the
+// output projection into ws.logits.  `k` only labels test taps (-1 = none); film_base / fg_base / fb_base are the
+// [layers][512] FiLM vectors and [layers][256] folded LN2 affine of this call's time embedding.
+static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* film_base, const float* fg_base,
+                        const float* fb_base, cudaStream_t st) {
+    const ddp_config& c = h->cfg;
+    const int Lc = c.num_layers, N = h->N, M = h->rows * h->N;
+    const bool seg = c.task == DDP_TASK_SEG;
+    const int C = seg ? c.num_classes : 1;
+    const bool s3 = h->nsplit == 3;
+    int rc;
+        for (int j = 0; j < Lc; ++j) {
+        const LayerW& L = h->L[j];
+        const float* film = film_base + (size_t)j * 2 * kE;
+        if (h->tc) {
+            const TcLayer& T = h->tcL[j];
+            {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
+                tc::EpiParams ep{};
+                ep.scale = T.v.inv_scale; ep.bias = L.bv; ep.out = ws.V; ep.ldc = kE; ep.ncols = kE;
+                TC_GEMM(h, DDP_K_VALUE, st, 256, tc::EPI_BIAS, h->mA_q, T.v, M, kE, ep);
+            }
+            {   // offsets / attention weights = proj(q + pos) = q W^T + pew
+                tc::EpiParams ep{};
+                bool want_s = false;
+                for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
+                ep.scale = T.s.inv_scale; ep.out = want_s ? ws.samp : nullptr; ep.ldc = kSampW; ep.ncols = kSampW;
+                ep.pew = h->pew[j]; ep.N_tok = N; ep.rec = ws.rec; ep.H = h->H; ep.W = h->W;
+                TC_GEMM(h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
+            }
+            if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
+            if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;   // written only when tapped
+            bool want_g = false;
+            for (const Tap& t : h->taps) want_g = want_g || (t.kind == DDP_TAP_GATHERED && t.step == k && t.layer == j);
+            KLAUNCH(h, DDP_K_GATHER, st,
+                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
+                        ws.V, ws.rec, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, N, h->W, M)));
+            if (want_g && (rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
+            {   // q = LN1(q + output_proj(g))
+                tc::EpiParams ep{};
+                ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = has_tap(h, DDP_TAP_LN1, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
+                ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                ep.ln_g = L.g1; ep.ln_b = L.e1;
+                TC_GEMM2(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
+            }
+            if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+            if (h->fuse_ffn) {   // q = FiLM(LN2(q + W2 gelu(W1 q + b1) + b2)) in ONE kernel, hidden activation kept in TMEM
+                tc::FfnParams fp{};
+                fp.s1_16 = T.f1.inv_scale * tc::kActScale; fp.s2 = T.f2.inv_scale; fp.b1 = L.b1; fp.b2 = L.b2;
+                fp.ln_g = fg_base + (size_t)j * kE; fp.ln_b = fb_base + (size_t)j * kE;
+                fp.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
+                fp.dbg = h->ffn_dbg;
+                prof_begin(h, DDP_K_FFN_FUSED, st);
+                cudaError_t e_ = s3 ? tc::launch_ffn_fused<3>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
+                                                              T.f2.map_alt_lo, M, fp, h->num_sms, st)
+                                    : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
+                                                              T.f2.map_alt_hi, M, fp, h->num_sms, st);
+                prof_end(h, st);
+                if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
+                LAUNCH_CHECK(h);
+            } else {
+            {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
+                tc::EpiParams ep{};
+                ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
+                ep.split = tc::SplitOut{ws.hid_hi, ws.hid_lo, kFFN};
+                TC_GEMM(h, DDP_K_FFN1, st, 256, tc::EPI_GELU, h->mA_q, T.f1, M, kFFN, ep);
+            }
+            {   // q = FiLM(LN2(q + hid W2^T + b2))
+                tc::EpiParams ep{};
+                ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
+                ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                ep.ln_g = fg_base + (size_t)j * kE; ep.ln_b = fb_base + (size_t)j * kE;
+                TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
+            }
+            }
+        } else {
+        {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
+            EpiBias epi{ws.V, L.bv, kE, kE, M};
+            KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
+        }
+        {   // offsets / attention weights = proj(q + pos) = q W^T + pew
+            EpiSampling epi{ws.samp, ws.rec, h->pew[j], N, h->H, h->W, M};
+            KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
+        }
+        if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
+        if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
+        KLAUNCH(h, DDP_K_GATHER, st,
+                (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.rec, ws.g, nullptr, nullptr, N, h->W, M)));
+        if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
+        {   // q = LN1(q + output_proj(g))
+            EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
+            KLAUNCH(h, DDP_K_OUT_PROJ, st, (launch_gemm_simt<256, false>(ws.g, kE, 0, L.Wo_t, kE, M, kE, kE, epi, st)));
+        }
+        if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+        {   // hid = gelu(q W1^T + b1)
+            EpiGelu epi{ws.hid, L.b1, kFFN, M};
+            KLAUNCH(h, DDP_K_FFN1, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.W1_t, kFFN, M, kE, kFFN, epi, st)));
+        }
+        {   // q = FiLM(LN2(q + hid W2^T + b2))
+            EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
+            KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
+        }
+        }
+        if ((rc = do_tap(h, DDP_TAP_LAYER_OUT, k, j, ws.q, (size_t)M * kE, st))) return rc;
+        if ((rc = do_tap(h, DDP_TAP_FILM, k, j, film, 2 * kE, st))) return rc;
+    }
+
+        if (h->tc) {
+        tc::EpiParams ep{};
+        ep.scale = h->tc_out.inv_scale; ep.bias = seg ? h->b_out : nullptr; ep.out = ws.logits;
+        ep.ldc = seg ? C : 16; ep.ncols = seg ? C : 9;
+        switch (h->out_bn) {
+            case 32: TC_GEMM(h, DDP_K_HEAD_OUT, st, 32, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 32, ep); break;
+            case 64: TC_GEMM(h, DDP_K_HEAD_OUT, st, 64, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 64, ep); break;
+            case 128: TC_GEMM(h, DDP_K_HEAD_OUT, st, 128, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 128, ep); break;
+            default: TC_GEMM(h, DDP_K_HEAD_OUT, st, 256, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 256, ep); break;
+        }
+    }
+    if (!h->tc) {
+        if (seg) {
+            EpiBias epi{ws.logits, h->b_out, C, C, M};
+            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 256, epi, st)));
+        } else {
+            EpiBias epi{ws.logits, nullptr, 16, 9, M};
+            KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 128, epi, st)));
+        }
+    }
+    (void)N;
+    return DDP_OK;
 }
 
 static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half* state_hi, __half* state_lo,
@@ -862,119 +998,10 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
         if ((rc = do_tap(h, DDP_TAP_HEAD_IN, k, -1, ws.q, (size_t)M * kE, st))) return rc;
         if ((rc = do_tap(h, DDP_TAP_TEMB, k, -1, h->temb + (size_t)k * kTimeDim, kTimeDim, st))) return rc;
 
-        for (int j = 0; j < Lc; ++j) {
-            const LayerW& L = h->L[j];
-            const float* film = h->film + ((size_t)k * Lc + j) * 2 * kE;
-            if (h->tc) {
-                const TcLayer& T = h->tcL[j];
-                {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
-                    tc::EpiParams ep{};
-                    ep.scale = T.v.inv_scale; ep.bias = L.bv; ep.out = ws.V; ep.ldc = kE; ep.ncols = kE;
-                    TC_GEMM(h, DDP_K_VALUE, st, 256, tc::EPI_BIAS, h->mA_q, T.v, M, kE, ep);
-                }
-                {   // offsets / attention weights = proj(q + pos) = q W^T + pew
-                    tc::EpiParams ep{};
-                    bool want_s = false;
-                    for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
-                    ep.scale = T.s.inv_scale; ep.out = want_s ? ws.samp : nullptr; ep.ldc = kSampW; ep.ncols = kSampW;
-                    ep.pew = h->pew[j]; ep.N_tok = N; ep.rec = ws.rec; ep.H = h->H; ep.W = h->W;
-                    TC_GEMM(h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
-                }
-                if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
-                if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;   // written only when tapped
-                bool want_g = false;
-                for (const Tap& t : h->taps) want_g = want_g || (t.kind == DDP_TAP_GATHERED && t.step == k && t.layer == j);
-                KLAUNCH(h, DDP_K_GATHER, st,
-                        (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
-                            ws.V, ws.rec, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, N, h->W, M)));
-                if (want_g && (rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
-                {   // q = LN1(q + output_proj(g))
-                    tc::EpiParams ep{};
-                    ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = has_tap(h, DDP_TAP_LN1, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
-                    ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                    ep.ln_g = L.g1; ep.ln_b = L.e1;
-                    TC_GEMM2(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
-                }
-                if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
-                if (h->fuse_ffn) {   // q = FiLM(LN2(q + W2 gelu(W1 q + b1) + b2)) in ONE kernel, hidden activation kept in TMEM
-                    tc::FfnParams fp{};
-                    fp.s1_16 = T.f1.inv_scale * tc::kActScale; fp.s2 = T.f2.inv_scale; fp.b1 = L.b1; fp.b2 = L.b2;
-                    fp.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; fp.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
-                    fp.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                    fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
-                    fp.dbg = h->ffn_dbg;
-                    prof_begin(h, DDP_K_FFN_FUSED, st);
-                    cudaError_t e_ = s3 ? tc::launch_ffn_fused<3>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
-                                                                  T.f2.map_alt_lo, M, fp, h->num_sms, st)
-                                        : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
-                                                                  T.f2.map_alt_hi, M, fp, h->num_sms, st);
-                    prof_end(h, st);
-                    if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
-                    LAUNCH_CHECK(h);
-                } else {
-                {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
-                    tc::EpiParams ep{};
-                    ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
-                    ep.split = tc::SplitOut{ws.hid_hi, ws.hid_lo, kFFN};
-                    TC_GEMM(h, DDP_K_FFN1, st, 256, tc::EPI_GELU, h->mA_q, T.f1, M, kFFN, ep);
-                }
-                {   // q = FiLM(LN2(q + hid W2^T + b2))
-                    tc::EpiParams ep{};
-                    ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
-                    ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                    ep.ln_g = h->film_g + ((size_t)k * Lc + j) * kE; ep.ln_b = h->film_b + ((size_t)k * Lc + j) * kE;
-                    TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
-                }
-                }
-            } else {
-            {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
-                EpiBias epi{ws.V, L.bv, kE, kE, M};
-                KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
-            }
-            {   // offsets / attention weights = proj(q + pos) = q W^T + pew
-                EpiSampling epi{ws.samp, ws.rec, h->pew[j], N, h->H, h->W, M};
-                KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
-            }
-            if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
-            if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
-            KLAUNCH(h, DDP_K_GATHER, st,
-                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.rec, ws.g, nullptr, nullptr, N, h->W, M)));
-            if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
-            {   // q = LN1(q + output_proj(g))
-                EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
-                KLAUNCH(h, DDP_K_OUT_PROJ, st, (launch_gemm_simt<256, false>(ws.g, kE, 0, L.Wo_t, kE, M, kE, kE, epi, st)));
-            }
-            if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
-            {   // hid = gelu(q W1^T + b1)
-                EpiGelu epi{ws.hid, L.b1, kFFN, M};
-                KLAUNCH(h, DDP_K_FFN1, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.W1_t, kFFN, M, kE, kFFN, epi, st)));
-            }
-            {   // q = FiLM(LN2(q + hid W2^T + b2))
-                EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
-                KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
-            }
-            }
-            if ((rc = do_tap(h, DDP_TAP_LAYER_OUT, k, j, ws.q, (size_t)M * kE, st))) return rc;
-            if ((rc = do_tap(h, DDP_TAP_FILM, k, j, film, 2 * kE, st))) return rc;
-        }
-
+        if ((rc = run_denoiser(h, ws, k, h->film + (size_t)k * Lc * 2 * kE, h->film_g + (size_t)k * Lc * kE,
+                               h->film_b + (size_t)k * Lc * kE, st))) return rc;
         const bool last = (k == T - 1);
-        if (h->tc) {
-            tc::EpiParams ep{};
-            ep.scale = h->tc_out.inv_scale; ep.bias = seg ? h->b_out : nullptr; ep.out = ws.logits;
-            ep.ldc = seg ? C : 16; ep.ncols = seg ? C : 9;
-            switch (h->out_bn) {
-                case 32: TC_GEMM(h, DDP_K_HEAD_OUT, st, 32, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 32, ep); break;
-                case 64: TC_GEMM(h, DDP_K_HEAD_OUT, st, 64, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 64, ep); break;
-                case 128: TC_GEMM(h, DDP_K_HEAD_OUT, st, 128, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 128, ep); break;
-                default: TC_GEMM(h, DDP_K_HEAD_OUT, st, 256, tc::EPI_BIAS, h->mA_q, h->tc_out, M, 256, ep); break;
-            }
-        }
         if (seg) {
-            if (!h->tc) {
-                EpiBias epi{ws.logits, h->b_out, C, C, M};
-                KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 256, epi, st)));
-            }
             if ((rc = do_tap(h, DDP_TAP_LOGITS, k, -1, ws.logits, (size_t)M * C, st))) return rc;
             SegStepParams p;
             p.logits = ws.logits; p.state = ws.state; p.accum = ws.accum; p.lut = h->lut;
@@ -986,10 +1013,6 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
             p.add_logits = (!c.accumulation && last) ? 1 : 0;
             KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
         } else {
-            if (!h->tc) {
-                EpiBias epi{ws.logits, nullptr, 16, 9, M};
-                KLAUNCH(h, DDP_K_HEAD_OUT, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, h->Wout_t, 256, M, kE, 128, epi, st)));
-            }
             DepthStepParams p;
             p.taps = ws.logits; p.state = ws.state; p.pred = ws.pred; p.out = out;
             p.H = h->H; p.W = h->W; p.R = R; p.B = B;
@@ -1039,6 +1062,60 @@ const char* ddp_kernel_class_name(int cls) {
                                              "ffn1_gelu", "ffn2_ln_film", "head_out", "step_update", "finalize", "layout",
                                              "ffn_fused"};
     return (cls >= 0 && cls < DDP_K_COUNT) ? names[cls] : nullptr;
+}
+
+int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embedding, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_head_forward: call ddp_plan first");
+    if (!feat || !time_embedding || !out || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_head_forward: null pointer");
+    if (workspace_bytes < h->ws_compute_bytes)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_head_forward: workspace %zu < required %zu", workspace_bytes, h->ws_compute_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_head_forward: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ddp_config& c = h->cfg;
+    const int Lc = c.num_layers, N = h->N, rows = h->rows, M = rows * N;
+    const bool seg = c.task == DDP_TASK_SEG;
+    h->launches = 0;
+    int rc;
+    Workspace ws;
+    carve(h, workspace, &ws, nullptr);
+    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws))) return rc;
+    // FiLM vectors of the caller's embedding: time_mlp = SiLU -> Linear(1024 -> 512) per layer (transformer.py:275-278, 413-417)
+    dim3 g2((2 * kE * 32 + 255) / 256, 1);
+    for (int j = 0; j < Lc; ++j) {
+        k_gemv<1, 0><<<g2, 256, 0, st>>>(h->L[j].Wt, h->L[j].bt, time_embedding, h->film_one + (size_t)j * 2 * kE, 2 * kE, kTimeDim,
+                                         kTimeDim, Lc * 2 * kE);
+        LAUNCH_CHECK(h);
+        k_fold_film<<<(kE + 255) / 256, 256, 0, st>>>(h->film_one + (size_t)j * 2 * kE, Lc * 2 * kE, h->L[j].g2, h->L[j].e2,
+                                                     h->fg_one + (size_t)j * kE, h->fb_one + (size_t)j * kE, Lc * kE, 1);
+        LAUNCH_CHECK(h);
+    }
+    // (rows, 256, h, w) -> tokens (+ fp16 planes)
+    {
+        dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
+        KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(feat, ws.q, kE, N)));
+        if (h->tc) {
+            size_t n8 = (size_t)M * kE / 8;
+            KLAUNCH(h, DDP_K_LAYOUT, st, (k_split_planes<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
+                                              ws.q, ws.q_hi, h->nsplit == 3 ? ws.q_lo : nullptr, n8)));
+        }
+    }
+    if ((rc = run_denoiser(h, ws, -1, h->film_one, h->fg_one, h->fb_one, st))) return rc;
+    if (seg) {          // logits tokens -> (rows, C, h, w)
+        const int C = c.num_classes;
+        dim3 grid((N + 31) / 32, (C + 31) / 32, rows), block(32, 8);
+        KLAUNCH(h, DDP_K_FINALIZE, st, (k_seg_finalize<<<grid, block, 0, st>>>(ws.logits, out, nullptr, N, C, 1.0f)));
+    } else {            // depth_pred = relu(conv3x3) + min_depth  (depth/.../decode_head.py:233-270)
+        DepthStepParams p;
+        p.taps = ws.logits; p.state = ws.state; p.pred = out; p.out = nullptr;
+        p.H = h->H; p.W = h->W; p.R = 1; p.B = rows;
+        p.conv_bias = h->conv_depth_bias; p.min_depth = c.min_depth; p.max_depth = c.max_depth; p.bit_scale = c.bit_scale;
+        p.gamma_now = 0.5f; p.gamma_next = 0.5f; p.last = 0;
+        KLAUNCH(h, DDP_K_STEP, st, (k_depth_step<<<(rows * N + 255) / 256, 256, 0, st>>>(p)));
+    }
+    return DDP_OK;
 }
 
 int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,

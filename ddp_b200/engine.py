@@ -153,6 +153,22 @@ class DecodeEngine:
                                         self._ws_ptr(), self._ws_bytes, stream))
         return (out, cls) if return_cls else out
 
+    def head_forward(self, feat: torch.Tensor, time_embedding: torch.Tensor):
+        """One denoiser call: feat (rows,256,h,w) CUDA fp32, time_embedding (1024,) -> (rows,C,h,w) logits / depth.
+        rows must be B*R of the current plan (plan(rows, 1, h, w) is made if there is none that fits)."""
+        rows, c, h, w = feat.shape
+        assert c == EMBED and feat.is_cuda and feat.dtype == torch.float32
+        if self._plan is None or self._plan[0] * self._plan[1] != rows or self._plan[2:] != (h, w):
+            self.plan(rows, 1, h, w)
+        feat = feat.contiguous()
+        temb = time_embedding.detach().to(feat.device, torch.float32).reshape(-1).contiguous()
+        assert temb.numel() == 4 * EMBED
+        out = torch.empty((rows, self.num_classes, h, w), dtype=torch.float32, device=feat.device)
+        stream = torch.cuda.current_stream(feat.device).cuda_stream
+        self._check(self.lib.ddp_head_forward(self._h, feat.data_ptr(), temb.data_ptr(), out.data_ptr(),
+                                              self._ws_ptr(), self._ws_bytes, stream))
+        return out
+
     def sample_host(self, x: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None,
                     cls: Optional[torch.Tensor] = None):
         """Host tensors in (ideally pinned), host tensors out; the copies are part of the call."""

@@ -210,8 +210,10 @@ class DDP(_DiffusionSegmentorBase):
         raise NotImplementedError("diffusion='ddpm' (ddp.py:248-290) is not built; no shipped config uses it")
 
     def _head_forward(self, feat, times):
-        raise NotImplementedError("single denoiser calls (decode_head.forward) are not exported by libddp_b200 yet; "
-                                  "the sampling loop is (ddim_sample)")
+        """decode_head.forward(inputs, times): one denoiser call through ddp_head_forward."""
+        if times.shape[0] != 1 and not bool((times == times[0:1]).all()):
+            raise NotImplementedError("one time embedding per call (the sampling loop uses the same t for every row)")
+        return self.engine().head_forward(feat.float(), times[0])
 
     def _decode_head_forward_test(self, x, t, img_metas):
         return self.decode_head.forward_test(x, t, img_metas, self.test_cfg)

@@ -74,7 +74,10 @@ class DDP(_DiffusionSegmentorBase):
         return self.engine().sample(x.float(), noise)
 
     def _head_forward(self, feat, times):
-        raise NotImplementedError("single denoiser calls are not exported by libddp_b200 yet")
+        """decode_head.forward(inputs, times): one denoiser call through ddp_head_forward."""
+        if times.shape[0] != 1 and not bool((times == times[0:1]).all()):
+            raise NotImplementedError("one time embedding per call (the sampling loop uses the same t for every row)")
+        return self.engine().head_forward(feat.float(), times[0])
 
     def simple_test(self, img, img_meta, rescale=True):
         depth_pred = self.encode_decode(img, img_meta, rescale)

@@ -142,6 +142,15 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
 int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* One evaluation of the denoiser, for callers of decode_head.forward(inputs, times)
+ * (segmentation/mmseg/models/decode_heads/deformable_head_with_time.py:90-132):
+ *   feat            (rows,256,h,w) fp32 NCHW device, rows = B*R of ddp_plan (the transform()/down() output)
+ *   time_embedding  [1024] fp32 device (one embedding for all rows, as in the sampling loop)
+ *   out             seg: (rows,C,h,w) logits; depth: (rows,1,h,w) = relu(conv3x3)+min_depth
+ * Uses (and clobbers) the same workspace as ddp_sample. */
+int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embedding, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies x and noise to the device, runs
  * ddp_sample, copies out (and cls) back and synchronises the stream.  Uses the tail of the workspace
  * for staging (ddp_plan's size already includes it). */

@@ -367,3 +367,23 @@ def test_fast_mode_reports_mismatch_rate():
     d = (out - ref).abs().max().item()
     print(f"tc_f16: max|d|={d:.3e}, class-map mismatches {bad}/{tot}")
     assert d < 0.1 and bad / tot < 0.02
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_decode_head_forward_single_call(mode):
+    """decode_head.forward(inputs, times) (deformable_head_with_time.py:90-132): one denoiser evaluation for a given
+    time embedding, against the oracle's head_seg / head_depth."""
+    model = _toy_model(timesteps=3, gemm_mode=mode)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=3)
+    W = O.make_weights(cfg, seed=17)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(3, 256, 9, 13, generator=g)
+    temb = torch.randn(1, 1024, generator=g)
+    with torch.no_grad():
+        want = O.head_seg(W, cfg, feat, temb)
+    got = model.decode_head([feat.cuda()], temb.cuda()).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < ATOL
+    check_class_map(got, want, f"decode_head.forward [{mode}]")
