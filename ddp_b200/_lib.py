@@ -21,7 +21,7 @@ TAP_HEAD_IN, TAP_VALUE, TAP_SAMPLING, TAP_GATHERED, TAP_LN1, TAP_LAYER_OUT, TAP_
 
 EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "ddp_weight_count",
            "ddp_weight_name", "ddp_set_weight", "ddp_commit_weights", "ddp_set_schedule",
-           "ddp_get_schedule", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_head_forward", "ddp_add_tap",
+           "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_head_forward", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
            "ddp_profile_collect", "ddp_kernel_class_name"]
 K_COUNT = 13
@@ -71,6 +71,8 @@ def load():
     lib.ddp_commit_weights.argtypes = [vp]
     lib.ddp_set_schedule.argtypes = [vp, i32, fp, fp, fp, fp, fp]
     lib.ddp_get_schedule.argtypes = [vp, fp, fp, fp, fp, fp]
+    lib.ddp_set_ddpm_schedule.argtypes = [vp, i32, fp, fp, fp, ctypes.POINTER(ctypes.c_int32)]
+    lib.ddp_set_step_noise.argtypes = [vp, vp]
     lib.ddp_plan.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
     lib.ddp_sample.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.ddp_sample_host.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]

@@ -91,6 +91,9 @@ struct ddp_handle {
 
     // schedule (host)
     std::vector<float> time_in, a_now, s_now, a_next, s_next;
+    std::vector<float> dd_omc, dd_c, dd_std;      // ddpm: (1 - c), c, exp(0.5 log variance) per step
+    std::vector<int> dd_noise_on;                 // ddpm: t_next > 0
+    const float* step_noise = nullptr;            // ddpm: caller's per-step noise (T, B, R, 256, h, w), device
     bool sched_override = false, time_dirty = true;
 
     std::vector<Tap> taps;
@@ -230,6 +233,7 @@ void default_schedule(ddp_handle* h) {
     const int T = c.timesteps;
     h->time_in.assign(T, 0.f); h->a_now.assign(T, 0.f); h->s_now.assign(T, 0.f);
     h->a_next.assign(T, 0.f); h->s_next.assign(T, 0.f);
+    h->dd_omc.assign(T, 1.f); h->dd_c.assign(T, 0.f); h->dd_std.assign(T, 0.f); h->dd_noise_on.assign(T, 0);
     for (int step = 0; step < T; ++step) {
         if (c.task == DDP_TASK_SEG) {
             double s0 = (double)c.sample_range_lo;
@@ -241,6 +245,15 @@ void default_schedule(ddp_handle* h) {
             h->time_in[step] = ln;
             h->a_now[step] = sqrtf(f_sigmoid(ln));  h->s_now[step] = sqrtf(f_sigmoid(-ln));
             h->a_next[step] = sqrtf(f_sigmoid(lx)); h->s_next[step] = sqrtf(f_sigmoid(-lx));
+            {   // ddpm scalars, ddp.py:274-278
+                volatile float dl = ln - lx;
+                volatile float cc = -expm1f(dl);
+                volatile float var = h->s_next[step] * h->s_next[step];
+                var = var * cc;
+                float lv = logf(var < 1e-20f ? 1e-20f : var);
+                h->dd_c[step] = cc; h->dd_omc[step] = 1.0f - cc; h->dd_std[step] = expf(0.5f * lv);
+                h->dd_noise_on[step] = t_next > 0 ? 1 : 0;
+            }
         } else {
             double t_now = 1 - (double)step / T;
             double t_next = 1 - (double)(step + 1 + c.time_difference) / T;
@@ -530,8 +543,10 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         return fail(nullptr, DDP_ERR_INVALID, "ddp_create: learned_sinusoidal_dim must be even and in [2, 30]");
     if (cfg->noise_schedule != DDP_SCHEDULE_COSINE && cfg->noise_schedule != DDP_SCHEDULE_LINEAR)
         return fail(nullptr, DDP_ERR_INVALID, "invalid noise schedule %d", cfg->noise_schedule);   // ddp.py:90 ValueError
-    if (cfg->diffusion != DDP_DIFFUSION_DDIM)
-        return fail(nullptr, DDP_ERR_UNSUPPORTED, "diffusion %d: only ddim is built", cfg->diffusion);   // ddp.py:123
+    if (cfg->diffusion != DDP_DIFFUSION_DDIM && cfg->diffusion != DDP_DIFFUSION_DDPM)
+        return fail(nullptr, DDP_ERR_UNSUPPORTED, "diffusion %d is neither ddim nor ddpm", cfg->diffusion);   // ddp.py:123 NotImplementedError
+    if (cfg->diffusion == DDP_DIFFUSION_DDPM && cfg->task != DDP_TASK_SEG)
+        return fail(nullptr, DDP_ERR_UNSUPPORTED, "ddpm is defined for the segmentation sampler only (the depth reference has no ddpm_step)");
     if (cfg->gemm_mode != DDP_GEMM_FP32 && cfg->gemm_mode != DDP_GEMM_TC_3XF16 && cfg->gemm_mode != DDP_GEMM_TC_F16)
         return fail(nullptr, DDP_ERR_INVALID, "ddp_create: invalid gemm_mode %d", cfg->gemm_mode);
     if (cfg->task == DDP_TASK_DEPTH && !(cfg->max_depth > cfg->min_depth))
@@ -700,6 +715,25 @@ int ddp_set_schedule(ddp_handle* h, int timesteps, const float* time_in, const f
     if (s_next) h->s_next.assign(s_next, s_next + timesteps);
     h->sched_override = true;
     h->time_dirty = true;
+    return DDP_OK;
+}
+
+int ddp_set_ddpm_schedule(ddp_handle* h, int timesteps, const float* one_minus_c, const float* c, const float* std_dev,
+                          const int32_t* noise_on) {
+    if (!h) return DDP_ERR_INVALID;
+    if (timesteps != h->cfg.timesteps)
+        return fail(h, DDP_ERR_INVALID, "ddp_set_ddpm_schedule: %d steps given, handle has %d", timesteps, h->cfg.timesteps);
+    if (!one_minus_c || !c || !std_dev || !noise_on) return fail(h, DDP_ERR_INVALID, "ddp_set_ddpm_schedule: null array");
+    h->dd_omc.assign(one_minus_c, one_minus_c + timesteps);
+    h->dd_c.assign(c, c + timesteps);
+    h->dd_std.assign(std_dev, std_dev + timesteps);
+    h->dd_noise_on.assign(noise_on, noise_on + timesteps);
+    return DDP_OK;
+}
+
+int ddp_set_step_noise(ddp_handle* h, const float* device_noise) {
+    if (!h) return DDP_ERR_INVALID;
+    h->step_noise = device_noise;
     return DDP_OK;
 }
 
@@ -962,6 +996,8 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
     const int C = seg ? c.num_classes : 1;
     h->launches = 0;
     int rc;
+    if (c.diffusion == DDP_DIFFUSION_DDPM && !h->step_noise)
+        return fail(h, DDP_ERR_STATE, "ddp_sample: diffusion=ddpm needs ddp_set_step_noise (the reference draws randn_like every step)");
     if (h->time_dirty && (rc = compute_time_constants(h, st))) return rc;
     Workspace ws;
     carve(h, workspace, &ws, nullptr);
@@ -1011,6 +1047,9 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
             p.alpha = h->a_now[k]; p.sigma = h->s_now[k]; p.alpha_next = h->a_next[k]; p.sigma_next = h->s_next[k];
             p.accumulate_prob = c.accumulation ? 1 : 0;
             p.add_logits = (!c.accumulation && last) ? 1 : 0;
+            p.ddpm = c.diffusion == DDP_DIFFUSION_DDPM ? 1 : 0;
+            p.one_minus_c = h->dd_omc[k]; p.c = h->dd_c[k]; p.std = h->dd_std[k];
+            p.step_noise = (p.ddpm && h->dd_noise_on[k]) ? h->step_noise + (size_t)k * M * kE : nullptr;
             KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
         } else {
             DepthStepParams p;

@@ -282,6 +282,10 @@ struct SegStepParams {
     float alpha, sigma, alpha_next, sigma_next;
     int accumulate_prob;   // accumulation=True: add softmax(logit) every step
     int add_logits;        // accumulation=False and last step: add raw logits
+    // ddpm_sample (ddp.py:248-290): m <- alpha' * (m * (1 - c) / alpha + c * m_hat) + std * noise
+    int ddpm;
+    float one_minus_c, c, std;
+    const float* step_noise;   // this step's noise, (rows, 256, h, w) NCHW, or null (t_next == 0: no noise)
 };
 
 // One warp per image token (b, n), looping over the R stochastic samples so that the accumulation
@@ -347,6 +351,19 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
             o.y = __fadd_rn(__fmul_rn(mh.y, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.y, -__fmul_rn(p.alpha, mh.y)), sig), p.sigma_next));
             o.z = __fadd_rn(__fmul_rn(mh.z, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.z, -__fmul_rn(p.alpha, mh.z)), sig), p.sigma_next));
             o.w = __fadd_rn(__fmul_rn(mh.w, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.w, -__fmul_rn(p.alpha, mh.w)), sig), p.sigma_next));
+            if (p.ddpm) {
+                const float mtv[4] = {mt.x, mt.y, mt.z, mt.w}, mhv[4] = {mh.x, mh.y, mh.z, mh.w};
+                float ov[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int ch = lane * 8 + h4 * 4 + e;
+                    const float nz = p.step_noise ? p.step_noise[((size_t)(b * p.R + r) * kE + ch) * p.N + n] : 0.f;
+                    const float mean = __fmul_rn(p.alpha_next, __fadd_rn(__fdiv_rn(__fmul_rn(mtv[e], p.one_minus_c), p.alpha),
+                                                                         __fmul_rn(p.c, mhv[e])));
+                    ov[e] = __fadd_rn(mean, __fmul_rn(p.std, nz));
+                }
+                o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+            }
             *reinterpret_cast<float4*>(st + h4 * 4) = o;
             nv[h4 * 4 + 0] = o.x; nv[h4 * 4 + 1] = o.y; nv[h4 * 4 + 2] = o.z; nv[h4 * 4 + 3] = o.w;
         }

@@ -43,6 +43,7 @@ class DecodeEngine:
         self.sample_range = tuple(sample_range)
         self.noise_schedule = noise_schedule
         self.accumulation = bool(accumulation)
+        self.diffusion = diffusion
         self.cin = EMBED if task == "seg" else 1
         self.cfg = L.DDPConfig(
             abi_version=L.ABI_VERSION, task=L.TASK_SEG if task == "seg" else L.TASK_DEPTH,
@@ -108,6 +109,10 @@ class DecodeEngine:
         if self.task == "seg":
             l, a, s, an, sn = S.seg_schedule(T, self.time_difference, self.sample_range, self.noise_schedule)
             self._check(self.lib.ddp_set_schedule(self._h, T, _fptr(l), _fptr(a), _fptr(s), _fptr(an), _fptr(sn)))
+            if self.diffusion == "ddpm":
+                omc, c, std, on = S.seg_ddpm_schedule(T, self.time_difference, self.sample_range, self.noise_schedule)
+                self._check(self.lib.ddp_set_ddpm_schedule(self._h, T, _fptr(omc), _fptr(c), _fptr(std),
+                                                           (ctypes.c_int32 * T)(*on)))
         else:
             t, g, gn = S.depth_schedule(T, self.time_difference)
             self._check(self.lib.ddp_set_schedule(self._h, T, _fptr(t), _fptr(g), None, _fptr(gn), None))
@@ -134,10 +139,18 @@ class DecodeEngine:
         return (p + 255) // 256 * 256
 
     # ------------------------------------------------------------------ the hot path
-    def sample(self, x: torch.Tensor, noise: torch.Tensor, return_cls=False):
+    def sample(self, x: torch.Tensor, noise: torch.Tensor, return_cls=False, step_noise: Optional[torch.Tensor] = None):
         """x (B,256,h,w), noise (B,R,Cin,h,w): CUDA fp32 tensors -> out (B,C,h,w) [, cls (B,h,w) int32].
+        diffusion='ddpm' also needs step_noise (T,B,R,256,h,w): what the reference draws with randn_like every step.
 
         Asynchronous on torch's current stream."""
+        if self.diffusion == "ddpm":
+            if step_noise is None:
+                raise ValueError("diffusion='ddpm' needs step_noise (T,B,R,256,h,w)")
+            step_noise = step_noise.contiguous()
+            assert step_noise.is_cuda and tuple(step_noise.shape) == (self.timesteps,) + tuple(noise.shape)
+            self._step_noise = step_noise
+            self._check(self.lib.ddp_set_step_noise(self._h, step_noise.data_ptr()))
         B, c, h, w = x.shape
         R = noise.shape[1]
         assert c == EMBED and tuple(noise.shape) == (B, R, self.cin, h, w), (x.shape, noise.shape)

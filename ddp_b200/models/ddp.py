@@ -167,6 +167,8 @@ class DDP(_DiffusionSegmentorBase):
         print(f" timesteps: {timesteps}, randsteps: {randsteps}, sample_range: {sample_range}, diffusion: {diffusion}")
         if noise_schedule not in ("linear", "cosine"):
             raise ValueError(f"invalid noise schedule {noise_schedule}")
+        if diffusion not in ("ddim", "ddpm"):
+            pass        # like the reference, an unknown sampler only fails when encode_decode is called (ddp.py:123)
         self.noise_schedule = noise_schedule
         c = self.decode_head.in_channels[0]
         if c != EMBED:
@@ -180,7 +182,7 @@ class DDP(_DiffusionSegmentorBase):
     def _engine_kwargs(self):
         return dict(task="seg", num_classes=self.num_classes, timesteps=self.timesteps,
                     time_difference=self.time_difference, sample_range=self.sample_range,
-                    noise_schedule=self.noise_schedule, diffusion="ddim", accumulation=self.accumulation,
+                    noise_schedule=self.noise_schedule, diffusion=self.diffusion, accumulation=self.accumulation,
                     bit_scale=self.bit_scale, learned_sinusoidal_dim=self.learned_sinusoidal_dim,
                     num_layers=self.decode_head.encoder.num_layers)
 
@@ -206,8 +208,16 @@ class DDP(_DiffusionSegmentorBase):
             noise = torch.randn((b, self.randsteps, c, h, w), device=x.device)
         return self.engine().sample(x.float(), noise)
 
-    def ddpm_sample(self, x, img_metas=None):
-        raise NotImplementedError("diffusion='ddpm' (ddp.py:248-290) is not built; no shipped config uses it")
+    @torch.no_grad()
+    def ddpm_sample(self, x, img_metas=None, noise=None, step_noise=None):
+        """ddp.py:248-290, batched.  The noise is drawn in the reference's order: the initial mask_t, then
+        randn_like(mask_t) at every step."""
+        b, c, h, w = x.shape
+        if noise is None:
+            noise = torch.randn((b, self.randsteps, c, h, w), device=x.device)
+        if step_noise is None:
+            step_noise = torch.stack([torch.randn_like(noise) for _ in range(self.timesteps)])
+        return self.engine().sample(x.float(), noise, step_noise=step_noise)
 
     def _head_forward(self, feat, times):
         """decode_head.forward(inputs, times): one denoiser call through ddp_head_forward."""

@@ -79,3 +79,20 @@ def depth_schedule(timesteps, time_difference):
         for c, v in zip(cols, (time[0:1], gamma(time[0:1]), gamma(time[1:2]))):
             c.append(float(v))
     return cols
+
+
+def seg_ddpm_schedule(timesteps, time_difference, sample_range, noise_schedule):
+    """ddpm_sample scalars (ddp.py:274-284): -> (1 - c, c, exp(0.5 log variance), t_next > 0) per step."""
+    fn = beta_linear_log_snr if noise_schedule == "linear" else alpha_cosine_log_snr
+    cols = [[], [], [], []]
+    for t_now, t_next in sampling_timesteps_seg(timesteps, time_difference, sample_range):
+        time = torch.tensor([t_now, t_next])
+        l_now, l_next = fn(time[0:1]), fn(time[1:2])
+        _, sigma_next = log_snr_to_alpha_sigma(l_next)
+        c = -expm1(l_now - l_next)
+        variance = (sigma_next ** 2) * c
+        std = (0.5 * log(variance)).exp()
+        for col, v in zip(cols, (1 - c, c, std)):
+            col.append(float(v))
+        cols[3].append(int(bool(time[1] > 0)))
+    return cols

@@ -124,6 +124,13 @@ int ddp_commit_weights(ddp_handle* h);
  * depth: time_in = t_now, a_now = gamma(t_now), a_next = gamma(t_next); s_* ignored. */
 int ddp_set_schedule(ddp_handle* h, int timesteps, const float* time_in, const float* a_now,
                      const float* s_now, const float* a_next, const float* s_next);
+/* diffusion = DDP_DIFFUSION_DDPM (ddp.py:248-290): per-step scalars (1 - c), c, exp(0.5 log variance) with
+ * c = -expm1(log_snr - log_snr_next), and whether t_next > 0 (noise is added).  Optional override like
+ * ddp_set_schedule.  ddp_set_step_noise hands over the noise the reference draws with randn_like(mask_t) every step:
+ * device fp32 (T, B, R, 256, h, w); it must be set before ddp_sample when diffusion is ddpm. */
+int ddp_set_ddpm_schedule(ddp_handle* h, int timesteps, const float* one_minus_c, const float* c, const float* std_dev,
+                          const int32_t* noise_on);
+int ddp_set_step_noise(ddp_handle* h, const float* device_noise);
 /* Read back the schedule in use (after ddp_plan). */
 int ddp_get_schedule(const ddp_handle* h, float* time_in, float* a_now, float* s_now,
                      float* a_next, float* s_next);

@@ -459,9 +459,10 @@ def sample_depth(W, cfg: OracleConfig, x, noise, trace: bool = False):
     return (out, traces) if trace else out
 
 
-def sample(W, cfg: OracleConfig, x, noise, trace: bool = False):
+def sample(W, cfg: OracleConfig, x, noise, trace: bool = False, ddpm_noise=None):
+    """ddpm_noise (B, T, R, 256, h, w): the per-step noise of diffusion='ddpm'."""
     if cfg.task == "seg":
-        return ddim_sample_seg(W, cfg, x, noise, trace)
+        return ddim_sample_seg(W, cfg, x, noise, trace, ddpm_noise)
     return sample_depth(W, cfg, x, noise, trace)
 
 

@@ -43,6 +43,9 @@ SEG_CASES = [
          T=1, R=1, h=64, w=64, wseed=14, xseed=104),
     dict(name="seg_city_T3_R3_ragged", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
          T=None, R=3, h=7, w=13, wseed=15, xseed=105),
+    # the stochastic sampler (ddp.py:248-290): diffusion='ddpm' is a constructor argument of the reference class
+    dict(name="seg_ddpm_T4_R2", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
+         T=4, R=2, h=10, w=12, wseed=16, xseed=106, diffusion="ddpm"),
 ]
 DEPTH_CASES = [
     dict(name="depth_nyu_T3", cfg="ddp_nyu/ddp_swint_1k_w7_nyu_bs2x8_scale01.py",
@@ -110,11 +113,13 @@ def run_seg():
         if case["T"] is not None:
             m.timesteps = case["T"]
         m.randsteps = case["R"]
+        diffusion = case.get("diffusion", "ddim")
+        m.diffusion = diffusion
         model = build_segmentor(m)
         model.eval()
         ocfg = O.OracleConfig(task="seg", num_classes=m.decode_head.num_classes, timesteps=m.timesteps,
                               randsteps=case["R"], bit_scale=m.bit_scale,
-                              accumulation=bool(m.get("accumulation", False)))
+                              accumulation=bool(m.get("accumulation", False)), diffusion=diffusion)
         W = O.make_weights(ocfg, seed=case["wseed"])
         load_weights(model, W)
         h, w, R = case["h"], case["w"], case["R"]
@@ -125,10 +130,10 @@ def run_seg():
         steps = []
         record_head(model, steps)
         torch.manual_seed(nseed)
-        out = model.ddim_sample(x, None)
+        out = model.ddim_sample(x, None) if diffusion == "ddim" else model.ddpm_sample(x, None)
         np.savez_compressed(
             os.path.join(HERE, case["name"] + ".npz"),
-            task="seg", model_type=m.type, config=case["cfg"], num_classes=ocfg.num_classes,
+            task="seg", model_type=m.type, diffusion=diffusion, config=case["cfg"], num_classes=ocfg.num_classes,
             timesteps=ocfg.timesteps, randsteps=R, bit_scale=ocfg.bit_scale,
             accumulation=ocfg.accumulation, h=h, w=w, wseed=case["wseed"], xseed=case["xseed"],
             nseed=nseed, x_checksum=checksum(x), noise_checksum=checksum(noise),

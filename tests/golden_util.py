@@ -30,7 +30,8 @@ def load_case(path):
     if task == "seg":
         cfg = O.OracleConfig(task="seg", num_classes=int(g["num_classes"]), timesteps=int(g["timesteps"]),
                              randsteps=int(g["randsteps"]), bit_scale=float(g["bit_scale"]),
-                             accumulation=bool(g["accumulation"]))
+                             accumulation=bool(g["accumulation"]),
+                             diffusion=str(g["diffusion"]) if "diffusion" in g else "ddim")
         cin = 256
     else:
         cfg = O.OracleConfig(task="depth", timesteps=int(g["timesteps"]), randsteps=int(g["randsteps"]),
@@ -43,6 +44,8 @@ def load_case(path):
     state = torch.get_rng_state()
     torch.manual_seed(int(g["nseed"]))
     noise = torch.randn((R, cin, h, w))[None]
+    if cfg.diffusion == "ddpm":       # the reference then draws randn_like(mask_t) once per step (ddp.py:279-283)
+        g["ddpm_noise"] = torch.stack([torch.randn((R, cin, h, w)) for _ in range(cfg.timesteps)])[None]   # (1,T,R,C,h,w)
     torch.set_rng_state(state)
     # the fixtures were produced from exactly these tensors
     assert np.allclose(checksum(x), g["x_checksum"], rtol=0, atol=1e-6), "x regeneration drifted"

@@ -19,7 +19,7 @@ def make_engine(cfg: O.OracleConfig, W, mode="fp32"):
     from ddp_b200 import DecodeEngine
     eng = DecodeEngine(task=cfg.task, num_classes=cfg.num_classes, timesteps=cfg.timesteps,
                        time_difference=cfg.time_difference, sample_range=cfg.sample_range,
-                       noise_schedule=cfg.noise_schedule, accumulation=cfg.accumulation,
+                       noise_schedule=cfg.noise_schedule, accumulation=cfg.accumulation, diffusion=cfg.diffusion,
                        bit_scale=cfg.bit_scale, num_layers=cfg.num_layers, min_depth=cfg.min_depth,
                        max_depth=cfg.max_depth, gemm_mode=mode)
     eng.load_state_dict(W)
@@ -77,7 +77,8 @@ def test_seg_matches_reference_golden(path, mode):
     eng = make_engine(cfg, W, mode)
     eng.plan(1, cfg.randsteps, x.shape[2], x.shape[3])
     taps = [eng.add_tap(6, k, -1, cfg.num_classes) for k in range(cfg.timesteps)]   # DDP_TAP_LOGITS
-    out, cls = eng.sample(x.cuda(), noise.cuda(), return_cls=True)
+    sn = g["ddpm_noise"][0][:, None].cuda() if cfg.diffusion == "ddpm" else None      # (T,1,R,256,h,w)
+    out, cls = eng.sample(x.cuda(), noise.cuda(), return_cls=True, step_noise=sn)
     torch.cuda.synchronize()
     ref = torch.from_numpy(g["out"])
     out = out.cpu()
@@ -387,3 +388,20 @@ def test_decode_head_forward_single_call(mode):
     assert got.shape == want.shape
     assert (got - want).abs().max().item() < ATOL
     check_class_map(got, want, f"decode_head.forward [{mode}]")
+
+
+def test_plugin_ddpm_sample_matches_oracle():
+    """diffusion='ddpm' (ddp.py:248-290): the plug-in draws the initial and the per-step noise in the reference's order."""
+    model = _toy_model(timesteps=4, randsteps=2, diffusion="ddpm")
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=4, randsteps=2, diffusion="ddpm")
+    W = O.make_weights(cfg, seed=19)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    x, _ = O.make_inputs(cfg, 2, 9, 11, seed=23)
+    torch.manual_seed(11)
+    out = model.ddpm_sample(x.cuda(), None).cpu()
+    torch.manual_seed(11)
+    noise = torch.randn((2, 2, 256, 9, 11), device="cuda")
+    steps = torch.stack([torch.randn_like(noise) for _ in range(4)])          # (T,B,R,256,h,w)
+    ref = O.sample(W, cfg, x, noise.cpu(), ddpm_noise=steps.permute(1, 0, 2, 3, 4, 5).cpu())
+    check_seg_output(out, ref, "plugin ddpm_sample")

@@ -16,12 +16,13 @@ def test_oracle_matches_reference_output(path):
     ref = torch.from_numpy(g["out"])
     # plain tensors: equal up to fp32 rounding order (torch's matmul folds a non-contiguous 3-D
     # input into one mm only when an operand has requires_grad, which nn.Parameter weights do)
-    out_plain = O.sample(W, cfg, x, noise)
+    dn = g.get("ddpm_noise")
+    out_plain = O.sample(W, cfg, x, noise, ddpm_noise=dn)
     assert out_plain.shape == ref.shape
     assert (out_plain - ref).abs().max().item() < 2e-5
     # with the reference's parameter flags the op sequence is identical: bit-for-bit
     W = {k: v.clone().requires_grad_(True) for k, v in W.items()}
-    out, traces = O.sample(W, cfg, x, noise, trace=True)
+    out, traces = O.sample(W, cfg, x, noise, trace=True, ddpm_noise=dn)
     # same ops in the same order on the same CPU: bit-for-bit
     assert torch.equal(out, ref), f"max |d| = {(out - ref).abs().max().item():.3e}"
     tr = traces[0]
