@@ -1157,6 +1157,18 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
     return DDP_OK;
 }
 
+int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int out_h, int out_w,
+                      uint8_t* cls, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!logits || !cls) return fail(h, DDP_ERR_INVALID, "ddp_resize_argmax: null pointer");
+    if (B < 1 || C < 1 || C > 256 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || out_h > 65535 || B > 65535)
+        return fail(h, DDP_ERR_INVALID, "ddp_resize_argmax: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((out_w + 127) / 128, out_h, B);
+    KLAUNCH(h, DDP_K_FINALIZE, st, (k_resize_argmax<<<grid, 128, 0, st>>>(logits, cls, C, in_h, in_w, out_h, out_w)));
+    return DDP_OK;
+}
+
 int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
                     void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return DDP_ERR_INVALID;

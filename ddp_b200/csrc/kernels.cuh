@@ -408,6 +408,33 @@ __global__ void k_seg_finalize(const float* __restrict__ accum, float* __restric
     }
 }
 
+// Post-loop tail: x4 bilinear resize (align_corners=False) + softmax + argmax of
+// EncoderDecoder.whole_inference / inference / simple_test (encoder_decoder.py:229-304, ddp.py:124-128) in one pass:
+// softmax is monotonic, so the class map is argmax_C of the resized logits; the (B,C,H,W) tensor is never materialised.
+// Interpolation follows ATen's upsample_bilinear2d: src = (dst + .5) * (in / out) - .5 clamped at 0, lambda = src - floor.
+__global__ void k_resize_argmax(const float* __restrict__ logits, uint8_t* __restrict__ cls, int C, int h, int w, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    float fy = __fadd_rn(__fmul_rn(sy, (float)y + 0.5f), -0.5f); fy = fy < 0.f ? 0.f : fy;
+    float fx = __fadd_rn(__fmul_rn(sx, (float)x + 0.5f), -0.5f); fx = fx < 0.f ? 0.f : fx;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.0f - ly, hx = 1.0f - lx;
+    const float* base = logits + (size_t)b * C * h * w;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+        const float* p = base + (size_t)c * h * w;
+        const float v = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, p[y0 * w + x0]), __fmul_rn(lx, p[y0 * w + x1]))),
+                                  __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, p[y1 * w + x0]), __fmul_rn(lx, p[y1 * w + x1]))));
+        if (v > best) { best = v; bi = c; }
+    }
+    cls[((size_t)b * H + y) * W + x] = (uint8_t)bi;
+}
+
 struct DepthStepParams {
     const float* taps;     // [rows][N][16]: per-token dot products with the 9 conv3x3 taps (cols 0..8)
     float* state;          // [rows][N] depth_t in/out

@@ -182,6 +182,16 @@ class DecodeEngine:
                                               self._ws_ptr(), self._ws_bytes, stream))
         return out
 
+    def resize_argmax(self, logits: torch.Tensor, size):
+        """(B,C,h,w) logits -> uint8 class map (B,H,W): bilinear resize + softmax + argmax in one kernel."""
+        B, C, h, w = logits.shape
+        H, W = int(size[0]), int(size[1])
+        logits = logits.contiguous()
+        cls = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
+        stream = torch.cuda.current_stream(logits.device).cuda_stream
+        self._check(self.lib.ddp_resize_argmax(self._h, logits.data_ptr(), B, C, h, w, H, W, cls.data_ptr(), stream))
+        return cls
+
     def sample_host(self, x: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None,
                     cls: Optional[torch.Tensor] = None):
         """Host tensors in (ideally pinned), host tensors out; the copies are part of the call."""

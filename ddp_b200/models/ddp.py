@@ -144,6 +144,7 @@ class DDP(_DiffusionSegmentorBase):
         super().__init__()
         self._engine = None
         self.gemm_mode = gemm_mode
+        self.fused_tail = True          # simple_test: fused resize+softmax+argmax kernel when the shapes allow it
         self._init_encoder(backbone, neck, pretrained)
         self.decode_head = build_head(decode_head)
         self.decode_head.__dict__['_owner'] = weakref.ref(self)     # not a submodule: no cycle in state_dict
@@ -252,6 +253,16 @@ class DDP(_DiffusionSegmentorBase):
         return output
 
     def simple_test(self, img, img_meta, rescale=True):
+        meta = img_meta[0]
+        plain = (not meta.get("flip", False) and (self.test_cfg or {}).get("mode", "whole") == "whole"
+                 and tuple(meta.get("img_shape", ())[:2]) == tuple(img.shape[2:])
+                 and (not rescale or tuple(meta.get("ori_shape", ())[:2]) == tuple(img.shape[2:])))
+        if self.fused_tail and plain and self.diffusion == "ddim":
+            # resize + softmax + argmax of encode_decode / whole_inference / inference in ONE kernel (the second
+            # resize of whole_inference is the identity when ori_shape == img_shape)
+            x = self.extract_feat(img)[0]
+            logits = self.ddim_sample(x, img_meta)
+            return list(self.engine().resize_argmax(logits, img.shape[2:]).cpu().numpy().astype("int64"))
         seg_logit = self.inference(img, img_meta, rescale)
         seg_pred = seg_logit.argmax(dim=1)
         return list(seg_pred.cpu().numpy())

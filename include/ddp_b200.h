@@ -158,6 +158,12 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
 int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embedding, float* out, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Post-loop tail in one kernel: bilinear resize (align_corners=False) of (B,C,h,w) logits to (out_h,out_w),
+ * softmax, argmax -> uint8 class map (B,out_h,out_w).  Replaces resize + F.softmax + argmax of
+ * segmentation/mmseg/models/segmentors/ddp.py:124-128 and encoder_decoder.py:232-304 for the no-flip, whole-image case. */
+int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int out_h, int out_w,
+                      uint8_t* cls, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies x and noise to the device, runs
  * ddp_sample, copies out (and cls) back and synchronises the stream.  Uses the tail of the workspace
  * for staging (ddp_plan's size already includes it). */

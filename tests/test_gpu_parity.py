@@ -405,3 +405,20 @@ def test_plugin_ddpm_sample_matches_oracle():
     steps = torch.stack([torch.randn_like(noise) for _ in range(4)])          # (T,B,R,256,h,w)
     ref = O.sample(W, cfg, x, noise.cpu(), ddpm_noise=steps.permute(1, 0, 2, 3, 4, 5).cpu())
     check_seg_output(out, ref, "plugin ddpm_sample")
+
+
+def test_fused_post_loop_tail_matches_torch():
+    """ddp_resize_argmax == argmax(softmax(F.interpolate(logits, bilinear, align_corners=False))) (encoder_decoder.py:229-304)."""
+    from ddp_b200 import DecodeEngine
+    eng = DecodeEngine(num_classes=19)
+    g = torch.Generator().manual_seed(1)
+    for (B, C, h, w, H, W) in [(2, 19, 32, 64, 128, 256), (1, 150, 16, 16, 64, 64), (1, 19, 7, 13, 30, 50), (1, 3, 5, 5, 5, 5)]:
+        logits = torch.randn(B, C, h, w, generator=g).cuda()
+        got = eng.resize_argmax(logits, (H, W)).long()
+        up = torch.nn.functional.interpolate(logits, size=(H, W), mode="bilinear", align_corners=False)
+        want = up.softmax(1).argmax(1)
+        diff = got != want
+        if diff.any():          # only exact-rounding ties may differ
+            top2 = up.topk(2, dim=1).values
+            assert float((top2[:, 0] - top2[:, 1])[diff].max()) < 1e-5
+        assert diff.float().mean().item() < 1e-4
