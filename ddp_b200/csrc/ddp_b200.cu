@@ -39,7 +39,7 @@ struct LayerW {
 struct TcWeight {
     __half *hi = nullptr, *lo = nullptr;
     CUtensorMap map_hi, map_lo;
-    CUtensorMap map_alt_hi, map_alt_lo;      // second box shape for the fused FFN kernel (W1: 64 rows, W2: 128 rows)
+    CUtensorMap map_alt_hi, map_alt_lo;      // second box shape for the fused FFN kernel (W1, W2: 128 rows)
     float inv_scale = 1.f;      // 1 / (2^shift * activation scale): multiplies the accumulator
     int rows_pad = 0, K = 0, bn = 0;
 };
@@ -425,7 +425,7 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
         if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st, kE))) return rc;
         if ((rc = make_tc_weight(h, T.f1, cur, kFFN, kE, 256, {{w1->dev, &w1->host, kFFN, kE, 1, 0, 0}}, st))) return rc;
         if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st, kE))) return rc;
-        if (!tc::make_map_f16(&T.f1.map_alt_hi, T.f1.hi, kFFN, kE, 64) || !tc::make_map_f16(&T.f1.map_alt_lo, T.f1.lo, kFFN, kE, 64) ||
+        if (!tc::make_map_f16(&T.f1.map_alt_hi, T.f1.hi, kFFN, kE, 128) || !tc::make_map_f16(&T.f1.map_alt_lo, T.f1.lo, kFFN, kE, 128) ||
             !tc::make_map_f16(&T.f2.map_alt_hi, T.f2.hi, kE, kFFN + kE, 128) || !tc::make_map_f16(&T.f2.map_alt_lo, T.f2.lo, kE, kFFN + kE, 128))
             return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fused-FFN weight maps");
     }

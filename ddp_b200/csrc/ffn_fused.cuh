@@ -2,16 +2,18 @@
 // with the 1024-wide hidden activation never leaving the SM (the unfused pair writes + reads 8 KB/token of it).
 //
 //   A1 = q planes (128 x 256, fp16 hi/lo)        shared memory, loaded once per tile by TMA
-//   for each chunk c of 64 hidden columns (16 chunks):
-//       D1 (TMEM, 128 x 64 fp32)  = A1 * W1[c]^T                       tcgen05.mma, A and B from shared memory
+//   for each chunk c of 128 hidden columns (8 chunks):
+//       D1 (TMEM, 128 x 128 fp32) = A1 * W1[c]^T                       tcgen05.mma, A and B from shared memory
 //       hid = gelu(D1 * s + b1)  -> fp16 hi/lo planes written back into TMEM (tcgen05.st, 2 halves per column)
 //       D2 (TMEM, 128 x 256 fp32) += hid * W2[:, c]^T                  tcgen05.mma with the A operand FROM TMEM
 //   D2 += A1 * (2^shift I)^T        (the residual, through the identity block of the augmented W2)
 //   epilogue: LayerNorm + folded FiLM, fp16 planes (and optionally fp32) of the new q
 //
-// TMEM (512 columns): D2 [0,256) | D1 x2 [256,384) | hid planes x2 [384,512) (hi 32 + lo 32 columns per buffer).
+// TMEM (512 columns): D2 [0,256) | D1 [256,384) | hid planes [384,512) (hi 64 + lo 64 columns).
+// The tensor core fetches shared-memory operands at ~64 B/clk, so an N=64 MMA1 (A 4 KB + B 2 KB per K=16 step) runs at a
+// third of its math rate; N=128 chunks halve that overhead, at the price of single-buffered D1 / hid (TMEM is full).
 // Warps: 0 TMA producer (A1 + a 4-stage ring of 16 KB weight units), 1 MMA issuer, 2..17 epilogue (thread = row,
-// four warps per TMEM lane quarter).  MMA1 of chunk c overlaps the GELU epilogue of chunk c-1 and MMA2 of chunk c-1.
+// four warps per TMEM lane quarter).  MMA1 of chunk c+1 overlaps the GELU epilogue and MMA2 of chunk c.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -69,7 +71,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                  const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ CUtensorMap mapW1lo,
                  const __grid_constant__ CUtensorMap mapW2hi, const __grid_constant__ CUtensorMap mapW2lo,
                  int M, FfnParams p) {
-    constexpr int kChunks = kFFN / 64;                  // 16
+    constexpr int kChunks = kFFN / 128;                 // 8
     constexpr int kPl = NSPLIT > 1 ? 2 : 1;             // planes per operand
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -81,10 +83,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     uint64_t* a1_empty = bars + 1;
     uint64_t* ring_full = bars + 2;                      // [4]
     uint64_t* ring_empty = bars + 6;                     // [4]
-    uint64_t* d1_full = bars + 10;                       // [2]
-    uint64_t* d1_empty = bars + 12;                      // [2]
-    uint64_t* a2_full = bars + 14;                       // [2]
-    uint64_t* a2_empty = bars + 16;                      // [2]
+    uint64_t* d1_full = bars + 10;
+    uint64_t* d1_empty = bars + 12;
+    uint64_t* a2_full = bars + 14;
+    uint64_t* a2_empty = bars + 16;
     uint64_t* d2_full = bars + 18;
     uint64_t* d2_empty = bars + 19;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
@@ -100,10 +102,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     if (warp == 1 && lane == 0) {
         mbar_init(a1_full, 1); mbar_init(a1_empty, 1);
         for (int s = 0; s < kFfnRing; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], 16);
-            mbar_init(&a2_full[b], 16); mbar_init(&a2_empty[b], 1);
-        }
+        mbar_init(d1_full, 1); mbar_init(d1_empty, 16);
+        mbar_init(a2_full, 16); mbar_init(a2_empty, 1);
         mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
         fence_barrier_init();
         fence_proxy_async();
@@ -128,11 +128,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 if (lo) tma_load_2d(st + bytes_each, lo, &ring_full[stage], c0, c1);
                 if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
             };
-            auto put_w2 = [&](int cc) {       // W2 columns of hidden chunk cc: (nh0: hi, lo), (nh1: hi, lo)
-                for (int nh = 0; nh < 2; ++nh) {
-                    put(&mapW2hi, nullptr, kFfnUnit, cc * 64, nh * 128);
-                    if (NSPLIT > 1) put(&mapW2lo, nullptr, kFfnUnit, cc * 64, nh * 128);
-                }
+            auto put_w2 = [&](int cc) {       // W2 columns of hidden chunk cc, per 64-wide K block and output half: hi, lo
+                for (int kb2 = 0; kb2 < 2; ++kb2)
+                    for (int nh = 0; nh < 2; ++nh) {
+                        put(&mapW2hi, nullptr, kFfnUnit, cc * 128 + kb2 * 64, nh * 128);
+                        if (NSPLIT > 1) put(&mapW2lo, nullptr, kFfnUnit, cc * 128 + kb2 * 64, nh * 128);
+                    }
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m0 = tile * BM;
@@ -143,8 +144,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                     if (NSPLIT > 1) tma_load_2d(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
                 }
                 for (int c = 0; c < kChunks; ++c) {
-                    for (int kb = 0; kb < 4; ++kb)       // W1 rows of hidden chunk c, K block kb: hi 8 KB | lo 8 KB
-                        put(&mapW1hi, NSPLIT > 1 ? &mapW1lo : nullptr, kFfnUnit / 2, kb * BK, c * 64);
+                    for (int kb = 0; kb < 4; ++kb) {     // W1 rows of hidden chunk c (128 rows), K block kb: hi unit, lo unit
+                        put(&mapW1hi, nullptr, kFfnUnit, kb * BK, c * 128);
+                        if (NSPLIT > 1) put(&mapW1lo, nullptr, kFfnUnit, kb * BK, c * 128);
+                    }
                     if (c >= 1) put_w2(c - 1);
                 }
                 put_w2(kChunks - 1);
@@ -157,18 +160,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp runs the loop; tcgen05 instructions on the elected lane) =====================
         {
-            constexpr uint32_t idesc64 = make_idesc(BM, 64);
             constexpr uint32_t idesc128 = make_idesc(BM, 128);
             int stage = 0; uint32_t rphase = 0, tphase = 0;
-            uint32_t d1e_phase[2] = {0, 0}, a2f_phase[2] = {0, 0};
-            uint32_t d2e_phase = 0;
+            uint32_t d1e_phase = 0, a2f_phase = 0, d2e_phase = 0;
             const uint32_t a1_addr = smem_u32(a1);
             long long tw_ring = 0, tw_d1e = 0, tw_a2f = 0, tw_d2e = 0, tw_a1 = 0, t_all = clock64();
-            auto ring_wait = [&]() -> uint32_t {
+            // wait for `n` consecutive ring units (n = 1 or 2) and return the address of the first; lo follows hi
+            auto ring_wait = [&](int n, uint32_t& second) -> uint32_t {
                 long long t0 = clock64();
                 mbar_wait(&ring_full[stage], rphase);
+                int s2 = stage + 1; uint32_t ph2 = rphase;
+                if (s2 == kFfnRing) { s2 = 0; ph2 ^= 1; }
+                if (n > 1) mbar_wait(&ring_full[s2], ph2);
                 tc_fence_after();
                 tw_ring += clock64() - t0;
+                second = smem_u32(ring + s2 * kFfnUnit);
                 return smem_u32(ring + stage * kFfnUnit);
             };
             auto ring_release = [&]() {
@@ -176,77 +182,68 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 __syncwarp();
                 if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
             };
-            auto mma2 = [&](int cc) {                    // D2 += hid(cc) * W2[:, cc]^T, hid planes in TMEM buffer cc & 1
-                const int b = cc & 1;
-                { long long t0 = clock64(); mbar_wait(&a2_full[b], a2f_phase[b]); a2f_phase[b] ^= 1; tw_a2f += clock64() - t0; }
+            auto mma2 = [&](int cc) {                    // D2 += hid(cc) * W2[:, cc]^T, hid planes in TMEM
+                { long long t0 = clock64(); mbar_wait(a2_full, a2f_phase); a2f_phase ^= 1; tw_a2f += clock64() - t0; }
                 tc_fence_after();
-                const uint32_t ahi = tA2 + 64 * b, alo = ahi + 32;
-                for (int nh = 0; nh < 2; ++nh) {
-                    const uint32_t uhi = ring_wait();
-                    const uint64_t bhi = make_smem_desc(uhi);
-                    const uint32_t d = tD2 + nh * 128;
-                    if (NSPLIT > 1) {
-                        // the lo unit sits in the next ring stage: peek it without releasing the hi unit
-                        int s2 = stage + 1; uint32_t ph2 = rphase;
-                        if (s2 == kFfnRing) { s2 = 0; ph2 ^= 1; }
-                        mbar_wait(&ring_full[s2], ph2);
-                        tc_fence_after();
-                        const uint64_t blo = make_smem_desc(smem_u32(ring + s2 * kFfnUnit));
+                const uint32_t ahi = tA2, alo = tA2 + 64;
+                for (int kb2 = 0; kb2 < 2; ++kb2)
+                    for (int nh = 0; nh < 2; ++nh) {
+                        uint32_t ulo;
+                        const uint32_t uhi = ring_wait(NSPLIT > 1 ? 2 : 1, ulo);
+                        const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(ulo);
+                        const uint32_t d = tD2 + nh * 128;
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                const uint32_t acc = (cc | k) != 0;
-                                umma_f16_ts(d, alo + 8 * k, bhi + 2 * k, idesc128, acc);
-                                umma_f16_ts(d, ahi + 8 * k, blo + 2 * k, idesc128, 1u);
-                                umma_f16_ts(d, ahi + 8 * k, bhi + 2 * k, idesc128, 1u);
+                                const uint32_t acc = (cc | kb2 | k) != 0;
+                                const uint32_t ka = 8 * (kb2 * 4 + k);
+                                if (NSPLIT > 1) {
+                                    umma_f16_ts(d, alo + ka, bhi + 2 * k, idesc128, acc);
+                                    umma_f16_ts(d, ahi + ka, blo + 2 * k, idesc128, 1u);
+                                    umma_f16_ts(d, ahi + ka, bhi + 2 * k, idesc128, 1u);
+                                } else {
+                                    umma_f16_ts(d, ahi + ka, bhi + 2 * k, idesc128, acc);
+                                }
                             }
                         }
                         __syncwarp();
                         ring_release();
-                        ring_release();
-                    } else {
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f16_ts(d, ahi + 8 * k, bhi + 2 * k, idesc128, (cc | k) != 0);
-                        }
-                        __syncwarp();
-                        ring_release();
+                        if (NSPLIT > 1) ring_release();
                     }
-                }
-                if (elect_one()) umma_commit(&a2_empty[b]);
+                if (elect_one()) umma_commit(a2_empty);
                 __syncwarp();
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 { long long t0 = clock64(); mbar_wait(a1_full, tphase); tw_a1 += clock64() - t0; }
                 tc_fence_after();
                 for (int c = 0; c <= kChunks; ++c) {
-                    if (c < kChunks) {                   // D1[c & 1] = A1 * W1[c]^T
-                        const int b = c & 1;
-                        { long long t0 = clock64(); mbar_wait(&d1_empty[b], d1e_phase[b] ^ 1); d1e_phase[b] ^= 1; tw_d1e += clock64() - t0; }
+                    if (c < kChunks) {                   // D1 = A1 * W1[c]^T   (N = 128)
+                        { long long t0 = clock64(); mbar_wait(d1_empty, d1e_phase ^ 1); d1e_phase ^= 1; tw_d1e += clock64() - t0; }
                         tc_fence_after();
-                        const uint32_t d = tD1 + 64 * b;
                         for (int kb = 0; kb < 4; ++kb) {
-                            const uint32_t u = ring_wait();
+                            uint32_t ulo;
+                            const uint32_t uhi = ring_wait(NSPLIT > 1 ? 2 : 1, ulo);
                             const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
                             const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
-                            const uint64_t bhi = make_smem_desc(u), blo = make_smem_desc(u + kFfnUnit / 2);
+                            const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(ulo);
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const uint32_t acc = (kb | k) != 0;
                                     if (NSPLIT > 1) {
-                                        umma_f16(d, alo + 2 * k, bhi + 2 * k, idesc64, acc);
-                                        umma_f16(d, ahi + 2 * k, blo + 2 * k, idesc64, 1u);
-                                        umma_f16(d, ahi + 2 * k, bhi + 2 * k, idesc64, 1u);
+                                        umma_f16(tD1, alo + 2 * k, bhi + 2 * k, idesc128, acc);
+                                        umma_f16(tD1, ahi + 2 * k, blo + 2 * k, idesc128, 1u);
+                                        umma_f16(tD1, ahi + 2 * k, bhi + 2 * k, idesc128, 1u);
                                     } else {
-                                        umma_f16(d, ahi + 2 * k, bhi + 2 * k, idesc64, acc);
+                                        umma_f16(tD1, ahi + 2 * k, bhi + 2 * k, idesc128, acc);
                                     }
                                 }
                             }
                             __syncwarp();
                             ring_release();
+                            if (NSPLIT > 1) ring_release();
                         }
-                        if (elect_one()) umma_commit(&d1_full[b]);
+                        if (elect_one()) umma_commit(d1_full);
                         __syncwarp();
                     }
                     if (c >= 1) {
@@ -262,7 +259,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                     const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
                     const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
                     for (int nh = 0; nh < 2; ++nh) {
-                        const uint64_t bi = make_smem_desc(ring_wait());
+                        uint32_t dummy;
+                        const uint64_t bi = make_smem_desc(ring_wait(1, dummy));
                         const uint32_t d = tD2 + nh * 128;
                         if (elect_one()) {
 #pragma unroll
@@ -299,27 +297,26 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         const int part = ew >> 2;                        // which quarter of the columns
         float* stg = reinterpret_cast<float*>(stage_tiles + ew * 2048);
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        uint32_t d1f_phase[2] = {0, 0}, a2e_phase[2] = {0, 0};
+        uint32_t d1f_phase = 0, a2e_phase = 0;
         uint32_t d2f_phase = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int m0 = tile * BM;
             const int wrow0 = m0 + q * 32;
             const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
-            // ---- per hidden chunk: GELU of this warp's 16 columns, planes back into TMEM ----
+            // ---- per hidden chunk: GELU of this warp's 32 columns, planes back into TMEM ----
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c) {
-                const int b = c & 1;
-                mbar_wait(&d1_full[b], d1f_phase[b]); d1f_phase[b] ^= 1;
+                mbar_wait(d1_full, d1f_phase); d1f_phase ^= 1;
                 tc_fence_after();
-                float v[16];
-                tmem_ld16(tD1 + 64 * b + part * 16 + lane_sel, v);
+                float v[32];
+                tmem_ld32(tD1 + part * 32 + lane_sel, v);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d1_empty[b]);            // D1[b] may be overwritten by MMA1 of chunk c + 2
-                uint32_t hi[8], lo[8];
-                const float* bp = p.b1 + c * 64 + part * 16;
+                if (lane == 0) mbar_arrive(d1_empty);                // D1 may be overwritten by MMA1 of chunk c + 1
+                uint32_t hi[16], lo[16];
+                const float* bp = p.b1 + c * 128 + part * 32;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i * 4));
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     float g[4];
@@ -349,15 +346,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         lo[i * 2 + 1] = *reinterpret_cast<const uint32_t*>(&l23);
                     }
                 }
-                // hid planes buffer b must have been consumed by MMA2 of chunk c - 2
-                mbar_wait(&a2_empty[b], a2e_phase[b] ^ 1); a2e_phase[b] ^= 1;
+                // the hid planes must have been consumed by MMA2 of chunk c - 1
+                mbar_wait(a2_empty, a2e_phase ^ 1); a2e_phase ^= 1;
                 tc_fence_after();
-                tmem_st8(tA2 + 64 * b + part * 8 + lane_sel, hi);
-                if (NSPLIT > 1) tmem_st8(tA2 + 64 * b + 32 + part * 8 + lane_sel, lo);
+                tmem_st8(tA2 + part * 16 + lane_sel, hi);
+                tmem_st8(tA2 + part * 16 + 8 + lane_sel, hi + 8);
+                if (NSPLIT > 1) {
+                    tmem_st8(tA2 + 64 + part * 16 + lane_sel, lo);
+                    tmem_st8(tA2 + 64 + part * 16 + 8 + lane_sel, lo + 8);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a2_full[b]);
+                if (lane == 0) mbar_arrive(a2_full);
             }
             // ---- final: LayerNorm (+ folded FiLM) of this warp's 64 columns of D2 ----
             mbar_wait(d2_full, d2f_phase); d2f_phase ^= 1;
