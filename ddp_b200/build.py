@@ -17,13 +17,24 @@ def nvcc_path():
     return p
 
 
-def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+STAMP = os.path.join(PKG, "libddp_b200.stamp")
+
+
+def source_digest():
+    """sha256 over the CUDA sources + the C header + the flags (mtimes do not survive the snapshot to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     csrc = os.path.join(PKG, "csrc")
-    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(PKG, "..", "include", "ddp_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    for f in sorted(os.listdir(csrc)) + [os.path.join("..", "..", "include", "ddp_b200.h")]:
+        with open(os.path.join(csrc, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def needs_build():
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    return open(STAMP).read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
@@ -36,6 +47,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_digest() + "\n")
     return LIB
 
 
