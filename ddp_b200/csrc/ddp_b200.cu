@@ -842,7 +842,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
     const int C = seg ? c.num_classes : 1;
     const bool s3 = h->nsplit == 3;
     int rc;
-        for (int j = 0; j < Lc; ++j) {
+    for (int j = 0; j < Lc; ++j) {
         const LayerW& L = h->L[j];
         const float* film = film_base + (size_t)j * 2 * kE;
         if (h->tc) {
@@ -865,8 +865,8 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
             bool want_g = false;
             for (const Tap& t : h->taps) want_g = want_g || (t.kind == DDP_TAP_GATHERED && t.step == k && t.layer == j);
             KLAUNCH(h, DDP_K_GATHER, st,
-                    (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
-                        ws.V, ws.rec, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, N, h->W, M)));
+            (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(
+            ws.V, ws.rec, want_g ? ws.g : nullptr, ws.g_hi, s3 ? ws.g_lo : nullptr, N, h->W, M)));
             if (want_g && (rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
             {   // q = LN1(q + output_proj(g))
                 tc::EpiParams ep{};
@@ -885,60 +885,60 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 fp.dbg = h->ffn_dbg;
                 prof_begin(h, DDP_K_FFN_FUSED, st);
                 cudaError_t e_ = s3 ? tc::launch_ffn_fused<3>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
-                                                              T.f2.map_alt_lo, M, fp, h->num_sms, st)
-                                    : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
-                                                              T.f2.map_alt_hi, M, fp, h->num_sms, st);
+                T.f2.map_alt_lo, M, fp, h->num_sms, st)
+                : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
+                T.f2.map_alt_hi, M, fp, h->num_sms, st);
                 prof_end(h, st);
                 if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
                 LAUNCH_CHECK(h);
             } else {
-            {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
-                tc::EpiParams ep{};
-                ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
-                ep.split = tc::SplitOut{ws.hid_hi, ws.hid_lo, kFFN};
-                TC_GEMM(h, DDP_K_FFN1, st, 256, tc::EPI_GELU, h->mA_q, T.f1, M, kFFN, ep);
-            }
-            {   // q = FiLM(LN2(q + hid W2^T + b2))
-                tc::EpiParams ep{};
-                ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
-                ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
-                ep.ln_g = fg_base + (size_t)j * kE; ep.ln_b = fb_base + (size_t)j * kE;
-                TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
-            }
+                {   // hid = gelu(q W1^T + b1), kept only as fp16 planes
+                    tc::EpiParams ep{};
+                    ep.scale = T.f1.inv_scale; ep.bias = L.b1; ep.out = nullptr; ep.ldc = kFFN; ep.ncols = kFFN;
+                    ep.split = tc::SplitOut{ws.hid_hi, ws.hid_lo, kFFN};
+                    TC_GEMM(h, DDP_K_FFN1, st, 256, tc::EPI_GELU, h->mA_q, T.f1, M, kFFN, ep);
+                }
+                {   // q = FiLM(LN2(q + hid W2^T + b2))
+                    tc::EpiParams ep{};
+                    ep.scale = T.f2.inv_scale; ep.bias = L.b2; ep.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
+                    ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
+                    ep.ln_g = fg_base + (size_t)j * kE; ep.ln_b = fb_base + (size_t)j * kE;
+                    TC_GEMM2(h, DDP_K_FFN2, st, 256, tc::EPI_RES_LN, h->mA_hid, h->mA_q, kFFN, T.f2, M, kE, ep);    // [hid | q] x [W2 | I]
+                }
             }
         } else {
-        {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
-            EpiBias epi{ws.V, L.bv, kE, kE, M};
-            KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
-        }
-        {   // offsets / attention weights = proj(q + pos) = q W^T + pew
-            EpiSampling epi{ws.samp, ws.rec, h->pew[j], N, h->H, h->W, M};
-            KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
-        }
-        if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
-        if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
-        KLAUNCH(h, DDP_K_GATHER, st,
-                (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.rec, ws.g, nullptr, nullptr, N, h->W, M)));
-        if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
-        {   // q = LN1(q + output_proj(g))
-            EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
-            KLAUNCH(h, DDP_K_OUT_PROJ, st, (launch_gemm_simt<256, false>(ws.g, kE, 0, L.Wo_t, kE, M, kE, kE, epi, st)));
-        }
-        if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
-        {   // hid = gelu(q W1^T + b1)
-            EpiGelu epi{ws.hid, L.b1, kFFN, M};
-            KLAUNCH(h, DDP_K_FFN1, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.W1_t, kFFN, M, kE, kFFN, epi, st)));
-        }
-        {   // q = FiLM(LN2(q + hid W2^T + b2))
-            EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
-            KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
-        }
+            {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
+                EpiBias epi{ws.V, L.bv, kE, kE, M};
+                KLAUNCH(h, DDP_K_VALUE, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.Wv_t, kE, M, kE, kE, epi, st)));
+            }
+            {   // offsets / attention weights = proj(q + pos) = q W^T + pew
+                EpiSampling epi{ws.samp, ws.rec, h->pew[j], N, h->H, h->W, M};
+                KLAUNCH(h, DDP_K_SAMPLING, st, (launch_gemm_simt<128, false>(ws.q, kE, 0, L.Ws_t, 128, M, kE, 128, epi, st)));
+            }
+            if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
+            if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;
+            KLAUNCH(h, DDP_K_GATHER, st,
+            (k_msda_gather<<<(unsigned)(((size_t)M * 32 + 255) / 256), 256, 0, st>>>(ws.V, ws.rec, ws.g, nullptr, nullptr, N, h->W, M)));
+            if ((rc = do_tap(h, DDP_TAP_GATHERED, k, j, ws.g, (size_t)M * kE, st))) return rc;
+            {   // q = LN1(q + output_proj(g))
+                EpiResidualLN epi{ws.q, ws.q, L.bo, L.g1, L.e1, nullptr, M};
+                KLAUNCH(h, DDP_K_OUT_PROJ, st, (launch_gemm_simt<256, false>(ws.g, kE, 0, L.Wo_t, kE, M, kE, kE, epi, st)));
+            }
+            if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
+            {   // hid = gelu(q W1^T + b1)
+                EpiGelu epi{ws.hid, L.b1, kFFN, M};
+                KLAUNCH(h, DDP_K_FFN1, st, (launch_gemm_simt<256, false>(ws.q, kE, 0, L.W1_t, kFFN, M, kE, kFFN, epi, st)));
+            }
+            {   // q = FiLM(LN2(q + hid W2^T + b2))
+                EpiResidualLN epi{ws.q, ws.q, L.b2, L.g2, L.e2, film, M};
+                KLAUNCH(h, DDP_K_FFN2, st, (launch_gemm_simt<256, false>(ws.hid, kFFN, 0, L.W2_t, kE, M, kFFN, kE, epi, st)));
+            }
         }
         if ((rc = do_tap(h, DDP_TAP_LAYER_OUT, k, j, ws.q, (size_t)M * kE, st))) return rc;
         if ((rc = do_tap(h, DDP_TAP_FILM, k, j, film, 2 * kE, st))) return rc;
     }
 
-        if (h->tc) {
+    if (h->tc) {
         tc::EpiParams ep{};
         ep.scale = h->tc_out.inv_scale; ep.bias = seg ? h->b_out : nullptr; ep.out = ws.logits;
         ep.ldc = seg ? C : 16; ep.ncols = seg ? C : 9;

@@ -97,3 +97,19 @@ def test_synthetic_recipe_equals_oracle_recipe():
         xa, na = O.make_inputs(cfg, 2, 5, 6, seed=3)
         xb, nb = S.make_inputs(task, 2, 2, 5, 6, seed=3)
         assert torch.equal(xa, xb) and torch.equal(na, nb)
+
+
+def test_ddpm_host_schedule_matches_oracle_formulas():
+    import torch
+    from ddp_b200 import schedule as S
+    from oracle import ddp_oracle as O
+    omc, c, std, on = S.seg_ddpm_schedule(4, 1, (0, 0.999), "cosine")
+    cfg = O.OracleConfig(timesteps=4)
+    for k, (t_now, t_next) in enumerate(O.time_pairs_seg(cfg)):
+        tt = torch.tensor([t_now, t_next])
+        ln, lx = O.log_snr_cosine(tt[0:1]), O.log_snr_cosine(tt[1:2])
+        cc = -torch.special.expm1(ln - lx)
+        _, sn = O.alpha_sigma(lx)
+        assert float(cc) == c[k] and float(1 - cc) == omc[k]
+        assert float((0.5 * torch.log(((sn ** 2) * cc).clamp(min=1e-20))).exp()) == std[k]
+        assert on[k] == int(t_next > 0)

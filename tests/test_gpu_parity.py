@@ -422,3 +422,18 @@ def test_fused_post_loop_tail_matches_torch():
             top2 = up.topk(2, dim=1).values
             assert float((top2[:, 0] - top2[:, 1])[diff].max()) < 1e-5
         assert diff.float().mean().item() < 1e-4
+
+
+def test_unfused_ffn_pair_still_correct(monkeypatch):
+    """DDP_B200_FUSE_FFN=0 selects the separate FFN1 (16-warp GELU epilogue) and FFN2 (LN + FiLM epilogue) kernels."""
+    monkeypatch.setenv("DDP_B200_FUSE_FFN", "0")
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    W = O.make_weights(cfg, seed=33)
+    x, noise = O.make_inputs(cfg, 2, 12, 16, seed=80)
+    ref = O.sample(W, cfg, x, noise)
+    eng = make_engine(cfg, W, "tc_3xf16")
+    eng.profile(True)
+    out = eng.sample(x.cuda(), noise.cuda()).cpu()
+    prof = eng.profile_collect()
+    assert prof["ffn1_gelu"][1] == 12 and prof["ffn2_ln_film"][1] == 12 and prof["ffn_fused"][1] == 0
+    check_seg_output(out, ref, "unfused FFN pair")
