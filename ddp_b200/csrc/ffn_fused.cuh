@@ -148,11 +148,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         put(&mapW1hi, nullptr, kFfnUnit, kb * BK, c * 128);
                         if (NSPLIT > 1) put(&mapW1lo, nullptr, kFfnUnit, kb * BK, c * 128);
                     }
+                    if (c == kChunks - 1)                // identity block of the augmented W2 (hi plane only): the residual
+                        for (int kb = 0; kb < 4; ++kb)   // is issued right after the last MMA1 (see the MMA warp)
+                            for (int nh = 0; nh < 2; ++nh) put(&mapW2hi, nullptr, kFfnUnit, kFFN + kb * BK, nh * 128);
                     if (c >= 1) put_w2(c - 1);
                 }
                 put_w2(kChunks - 1);
-                for (int kb = 0; kb < 4; ++kb)           // identity block of the augmented W2 (hi plane only)
-                    for (int nh = 0; nh < 2; ++nh) put(&mapW2hi, nullptr, kFfnUnit, kFFN + kb * BK, nh * 128);
                 tphase ^= 1;
             }
         }
@@ -246,6 +247,29 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         if (elect_one()) umma_commit(d1_full);
                         __syncwarp();
                     }
+                    if (c == kChunks - 1) {              // last MMA1 issued: add the residual now and release q's planes early
+                    // residual: D2 += q * (2^shift I)^T with q's planes still in shared memory
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
+                        const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
+                        for (int nh = 0; nh < 2; ++nh) {
+                            uint32_t dummy;
+                            const uint64_t bi = make_smem_desc(ring_wait(1, dummy));
+                            const uint32_t d = tD2 + nh * 128;
+                            if (elect_one()) {
+    #pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (NSPLIT > 1) umma_f16(d, alo + 2 * k, bi + 2 * k, idesc128, 1u);
+                                    umma_f16(d, ahi + 2 * k, bi + 2 * k, idesc128, 1u);
+                                }
+                            }
+                            __syncwarp();
+                            ring_release();
+                        }
+                    }
+                        if (elect_one()) umma_commit(a1_empty);   // q planes may be overwritten by the next tile's load
+                        __syncwarp();
+                    }
                     if (c >= 1) {
                         if (c == 1) {                    // D2 of the previous tile must have been drained
                             { long long t0 = clock64(); mbar_wait(d2_empty, d2e_phase ^ 1); d2e_phase ^= 1; tw_d2e += clock64() - t0; }
@@ -254,29 +278,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         mma2(c - 1);
                     }
                 }
-                // residual: D2 += q * (2^shift I)^T with q's planes still in shared memory
-                for (int kb = 0; kb < 4; ++kb) {
-                    const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
-                    const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
-                    for (int nh = 0; nh < 2; ++nh) {
-                        uint32_t dummy;
-                        const uint64_t bi = make_smem_desc(ring_wait(1, dummy));
-                        const uint32_t d = tD2 + nh * 128;
-                        if (elect_one()) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (NSPLIT > 1) umma_f16(d, alo + 2 * k, bi + 2 * k, idesc128, 1u);
-                                umma_f16(d, ahi + 2 * k, bi + 2 * k, idesc128, 1u);
-                            }
-                        }
-                        __syncwarp();
-                        ring_release();
-                    }
-                }
-                if (elect_one()) {
-                    umma_commit(a1_empty);               // q planes may be overwritten by the next tile's load
-                    umma_commit(d2_full);
-                }
+                if (elect_one()) umma_commit(d2_full);
                 __syncwarp();
                 tphase ^= 1;
             }

@@ -437,3 +437,31 @@ def test_unfused_ffn_pair_still_correct(monkeypatch):
     prof = eng.profile_collect()
     assert prof["ffn1_gelu"][1] == 12 and prof["ffn2_ln_film"][1] == 12 and prof["ffn_fused"][1] == 0
     check_seg_output(out, ref, "unfused FFN pair")
+
+
+def test_full_size_single_step_against_oracle():
+    """BASELINE config-3 token grid (128 x 256 = 32768 tokens, 19 classes), one image, one DDIM step: the whole
+    per-step path at full size against the oracle (about 10-20 s of CPU work)."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=1)
+    W = O.make_weights(cfg, seed=41)
+    x, noise = O.make_inputs(cfg, 1, 128, 256, seed=90)
+    ref = O.sample(W, cfg, x, noise)
+    out = make_engine(cfg, W, "tc_3xf16").sample(x.cuda(), noise.cuda()).cpu()
+    d = (out - ref).abs()
+    print(f"full-size step: max|d|={d.max().item():.2e} mean|d|={d.mean().item():.2e}")
+    assert d.max().item() < ATOL
+    check_class_map(out, ref, "full-size 128x256 single step [tc_3xf16]")
+
+
+def test_full_size_depth_properties():
+    """NYU shape (120 x 160 tokens), T=20: output inside [min_depth, max_depth], deterministic, batch = per-image."""
+    cfg = O.OracleConfig(task="depth", timesteps=20, bit_scale=0.1)
+    W = O.make_weights(cfg, seed=42)
+    x, noise = O.make_inputs(cfg, 2, 120, 160, seed=91)
+    eng = make_engine(cfg, W, "tc_3xf16")
+    a = eng.sample(x.cuda(), noise.cuda())
+    b = eng.sample(x.cuda(), noise.cuda())
+    assert torch.equal(a, b)
+    assert a.min().item() >= cfg.min_depth - 1e-7 and a.max().item() <= cfg.max_depth + 1e-6
+    solo = eng.sample(x[1:2].cuda(), noise[1:2].cuda())
+    assert torch.equal(solo, a[1:2])
