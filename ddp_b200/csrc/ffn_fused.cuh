@@ -34,8 +34,10 @@ struct FfnParams {
 
 constexpr int kFfnThreads = 32 * 18;
 constexpr int kFfnUnit = 16384;
-constexpr int kFfnRing = 4;
-constexpr int kFfnSmem = 8 * kFfnUnit + kFfnRing * kFfnUnit + kStageAreaBytes + 1024 + 256;
+constexpr int kFfnRing = 5;               // 80 KB of weight tiles in flight (64 KB left the MMA warp waiting 22 % of its time)
+constexpr int kFfnStageTile = 1024;       // per-warp store staging tile (32 rows x 32 bytes)
+constexpr int kFfnStageArea = 16 * kFfnStageTile;
+constexpr int kFfnSmem = 8 * kFfnUnit + kFfnRing * kFfnUnit + kFfnStageArea + 1024 + 256;
 static_assert(kFfnSmem <= 232448, "fused FFN kernel exceeds shared memory");
 
 // tcgen05.mma with the A operand in tensor memory (lane = row, two fp16 K-elements per 32-bit column)
@@ -65,6 +67,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
+// 32 rows x 32 bytes through a 1 KB tile: `h` = the row's 32 bytes as 2 uint4; dst / ld in halves
+__device__ __forceinline__ void stage_store_32b(float* stg, const uint4* h, __half* dst, int ld, int rows_valid, int lane) {
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+    s16[lane * 2 + (0 ^ ((lane >> 2) & 1))] = h[0];
+    s16[lane * 2 + (1 ^ ((lane >> 2) & 1))] = h[1];
+    __syncwarp();
+    const int c = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = (lane >> 1) + 16 * i;
+        uint4 x = s16[r * 2 + (c ^ ((r >> 2) & 1))];
+        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c * 8) = x;
+    }
+    __syncwarp();
+}
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_constant__ CUtensorMap mapA1lo,
@@ -78,18 +96,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     uint8_t* a1 = smem;                                  // [plane][kb] 16 KB tiles
     uint8_t* ring = smem + 8 * kFfnUnit;
     uint8_t* stage_tiles = ring + kFfnRing * kFfnUnit;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + kStageAreaBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + kFfnStageArea);
     uint64_t* a1_full = bars + 0;
     uint64_t* a1_empty = bars + 1;
-    uint64_t* ring_full = bars + 2;                      // [4]
-    uint64_t* ring_empty = bars + 6;                     // [4]
-    uint64_t* d1_full = bars + 10;
-    uint64_t* d1_empty = bars + 12;
-    uint64_t* a2_full = bars + 14;
-    uint64_t* a2_empty = bars + 16;
-    uint64_t* d2_full = bars + 18;
-    uint64_t* d2_empty = bars + 19;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* ring_full = bars + 2;                      // [kFfnRing <= 8]
+    uint64_t* ring_empty = bars + 10;                    // [kFfnRing <= 8]
+    uint64_t* d1_full = bars + 18;
+    uint64_t* d1_empty = bars + 19;
+    uint64_t* a2_full = bars + 20;
+    uint64_t* a2_empty = bars + 21;
+    uint64_t* d2_full = bars + 22;
+    uint64_t* d2_empty = bars + 23;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    static_assert(kFfnRing <= 8, "barrier slots");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -297,7 +316,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         const int ew = warp - 2;
         const int q = warp & 3;
         const int part = ew >> 2;                        // which quarter of the columns
-        float* stg = reinterpret_cast<float*>(stage_tiles + ew * 2048);
+        float* stg = reinterpret_cast<float*>(stage_tiles + ew * kFfnStageTile);
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         uint32_t d1f_phase = 0, a2e_phase = 0;
         uint32_t d2f_phase = 0;
@@ -392,7 +411,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
             }
             {   // combine the four column quarters of each row: every warp of the lane quarter gets all four partials
                 for (int w = 0; w < 4; ++w) {
-                    float2* dst = reinterpret_cast<float2*>(stage_tiles + (w * 4 + (ew & 3)) * 2048);
+                    float2* dst = reinterpret_cast<float2*>(stage_tiles + (w * 4 + (ew & 3)) * kFfnStageTile);
                     dst[part * 32 + lane] = make_float2(mean, m2);
                 }
                 named_bar_sync(1 + q, 128);
@@ -425,27 +444,30 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                     v[i * 4 + 2] = fmaf((v[i * 4 + 2] - mean) * rstd, g4.z, b4.z);
                     v[i * 4 + 3] = fmaf((v[i * 4 + 3] - mean) * rstd, g4.w, b4.w);
                 }
-                uint4 hi[4], lo[4];
-                __half2* h2 = reinterpret_cast<__half2*>(hi);
-                __half2* l2 = reinterpret_cast<__half2*>(lo);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a = v[2 * i] * kActScale, bq = v[2 * i + 1] * kActScale;
-                    const __half2 hh = __floats2half2_rn(a, bq);
-                    h2[i] = hh;
-                    if (NSPLIT > 1) {
-                        const float2 back = __half22float2(hh);
-                        l2[i] = __floats2half2_rn(a - back.x, bq - back.y);
+                for (int sub = 0; sub < 2; ++sub) {          // 16 columns (32-byte plane rows) per staging round
+                    uint4 hi[2], lo[2];
+                    __half2* h2 = reinterpret_cast<__half2*>(hi);
+                    __half2* l2 = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a = v[sub * 16 + 2 * i] * kActScale, bq = v[sub * 16 + 2 * i + 1] * kActScale;
+                        const __half2 hh = __floats2half2_rn(a, bq);
+                        h2[i] = hh;
+                        if (NSPLIT > 1) {
+                            const float2 back = __half22float2(hh);
+                            l2[i] = __floats2half2_rn(a - back.x, bq - back.y);
+                        }
                     }
+                    const size_t o = (size_t)wrow0 * p.split.ld + col + sub * 16;
+                    stage_store_32b(stg, hi, p.split.hi + o, p.split.ld, rows_valid, lane);
+                    if (NSPLIT > 1) stage_store_32b(stg, lo, p.split.lo + o, p.split.ld, rows_valid, lane);
                 }
-                stage_store_f16_32(stg, hi, p.split.hi + (size_t)wrow0 * p.split.ld + col, p.split.ld, rows_valid, lane);
-                if (NSPLIT > 1)
-                    stage_store_f16_32(stg, lo, p.split.lo + (size_t)wrow0 * p.split.ld + col, p.split.ld, rows_valid, lane);
-                if (p.out) {                             // fp32 copy for test taps: 16 columns (64-byte rows) at a time
-                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[0]),
-                                       reinterpret_cast<__half*>(p.out + (size_t)wrow0 * kE + col), 2 * kE, rows_valid, lane);
-                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[16]),
-                                       reinterpret_cast<__half*>(p.out + (size_t)wrow0 * kE + col + 16), 2 * kE, rows_valid, lane);
+                if (p.out) {                                 // fp32 copy for test taps: 8 columns (32-byte rows) at a time
+#pragma unroll
+                    for (int s8 = 0; s8 < 4; ++s8)
+                        stage_store_32b(stg, reinterpret_cast<const uint4*>(&v[s8 * 8]),
+                                        reinterpret_cast<__half*>(p.out + (size_t)wrow0 * kE + col + s8 * 8), 2 * kE, rows_valid, lane);
                 }
             }
             tc_fence_before();
