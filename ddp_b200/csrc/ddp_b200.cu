@@ -40,6 +40,7 @@ struct TcWeight {
     __half *hi = nullptr, *lo = nullptr;
     CUtensorMap map_hi, map_lo;
     CUtensorMap map_alt_hi, map_alt_lo;      // second box shape for the fused FFN kernel (W1, W2: 128 rows)
+    CUtensorMap map_half_hi, map_half_lo;    // 64-row boxes: one pair member's half of a weight tile (CTA-pair fused FFN)
     float inv_scale = 1.f;      // 1 / (2^shift * activation scale): multiplies the accumulator
     int rows_pad = 0, K = 0, bn = 0;
 };
@@ -70,6 +71,7 @@ struct ddp_handle {
     // tcgen05 path (gemm_mode != FP32)
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
+    bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
     unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
     int nsplit = 1;
     int num_sms = 148;
@@ -428,6 +430,9 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
         if (!tc::make_map_f16(&T.f1.map_alt_hi, T.f1.hi, kFFN, kE, 128) || !tc::make_map_f16(&T.f1.map_alt_lo, T.f1.lo, kFFN, kE, 128) ||
             !tc::make_map_f16(&T.f2.map_alt_hi, T.f2.hi, kE, kFFN + kE, 128) || !tc::make_map_f16(&T.f2.map_alt_lo, T.f2.lo, kE, kFFN + kE, 128))
             return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fused-FFN weight maps");
+        if (!tc::make_map_f16(&T.f1.map_half_hi, T.f1.hi, kFFN, kE, 64) || !tc::make_map_f16(&T.f1.map_half_lo, T.f1.lo, kFFN, kE, 64) ||
+            !tc::make_map_f16(&T.f2.map_half_hi, T.f2.hi, kE, kFFN + kE, 64) || !tc::make_map_f16(&T.f2.map_half_lo, T.f2.lo, kE, kFFN + kE, 64))
+            return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fused-FFN half-tile maps");
     }
     if (seg) {
         WeightSpec* w = spec("decode_head.conv_seg.weight");
@@ -570,6 +575,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
     {
         const char* e = getenv("DDP_B200_FUSE_FFN");
         h->fuse_ffn = h->tc && (e == nullptr || atoi(e) != 0);
+        const char* pe = getenv("DDP_B200_FFN_PAIR");
+        h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         const char* d = getenv("DDP_B200_FFN_DBG");
         if (d && atoi(d) != 0 && cudaMalloc(&h->ffn_dbg, 64) == cudaSuccess) cudaMemset(h->ffn_dbg, 0, 64);
     }
@@ -823,8 +830,8 @@ int64_t ddp_last_launch_count(const ddp_handle* h) {
     if (h && h->ffn_dbg) {          // profiling aid: dump and reset the MMA-issuer cycle counters
         unsigned long long v[8];
         if (cudaMemcpy(v, h->ffn_dbg, 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
-            fprintf(stderr, "[ffn_fused issuer cycles] total %llu ring_wait %llu d1_empty %llu a2_full %llu d2_empty %llu a1_full %llu\n",
-                    v[0], v[1], v[2], v[3], v[4], v[5]);
+            fprintf(stderr, "[ffn_fused issuer cycles] total %llu ring_wait %llu d1_empty %llu a2_full %llu d2_empty %llu a1_full %llu issue1 %llu issue2 %llu\n",
+                    v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
             cudaMemset(h->ffn_dbg, 0, 64);
         }
     }
@@ -884,10 +891,17 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
                 fp.dbg = h->ffn_dbg;
                 prof_begin(h, DDP_K_FFN_FUSED, st);
-                cudaError_t e_ = s3 ? tc::launch_ffn_fused<3>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
-                T.f2.map_alt_lo, M, fp, h->num_sms, st)
-                : tc::launch_ffn_fused<1>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
-                T.f2.map_alt_hi, M, fp, h->num_sms, st);
+                cudaError_t e_;
+                if (h->ffn_pair)
+                    e_ = s3 ? tc::launch_ffn_fused<3, true>(h->mA_q[0], h->mA_q[1], T.f1.map_half_hi, T.f1.map_half_lo, T.f2.map_half_hi,
+                                                            T.f2.map_half_lo, M, fp, h->num_sms, st)
+                            : tc::launch_ffn_fused<1, true>(h->mA_q[0], h->mA_q[0], T.f1.map_half_hi, T.f1.map_half_hi, T.f2.map_half_hi,
+                                                            T.f2.map_half_hi, M, fp, h->num_sms, st);
+                else
+                    e_ = s3 ? tc::launch_ffn_fused<3, false>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
+                                                             T.f2.map_alt_lo, M, fp, h->num_sms, st)
+                            : tc::launch_ffn_fused<1, false>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
+                                                             T.f2.map_alt_hi, M, fp, h->num_sms, st);
                 prof_end(h, st);
                 if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
                 LAUNCH_CHECK(h);

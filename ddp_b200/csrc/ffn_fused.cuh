@@ -16,6 +16,7 @@
 // four warps per TMEM lane quarter).  MMA1 of chunk c+1 overlaps the GELU epilogue and MMA2 of chunk c.
 #pragma once
 #include "gemm_tc.cuh"
+#include "cta_pair.cuh"
 
 namespace ddp {
 namespace tc {
@@ -34,10 +35,10 @@ struct FfnParams {
 
 constexpr int kFfnThreads = 32 * 18;
 constexpr int kFfnUnit = 16384;
-constexpr int kFfnRing = 5;               // 80 KB of weight tiles in flight (64 KB left the MMA warp waiting 22 % of its time)
+constexpr int kFfnRingBytes = 5 * kFfnUnit;   // weight tiles in flight (a unit = hi + lo plane of one [128 x 64] tile, or a pair member's halves)
 constexpr int kFfnStageTile = 1024;       // per-warp store staging tile (32 rows x 32 bytes)
 constexpr int kFfnStageArea = 16 * kFfnStageTile;
-constexpr int kFfnSmem = 8 * kFfnUnit + kFfnRing * kFfnUnit + kFfnStageArea + 1024 + 256;
+constexpr int kFfnSmem = 8 * kFfnUnit + kFfnRingBytes + kFfnStageArea + 1024 + 256;
 static_assert(kFfnSmem <= 232448, "fused FFN kernel exceeds shared memory");
 
 // tcgen05.mma with the A operand in tensor memory (lane = row, two fp16 K-elements per 32-bit column)
@@ -83,7 +84,12 @@ __device__ __forceinline__ void stage_store_32b(float* stg, const uint4* h, __ha
     __syncwarp();
 }
 
-template <int NSPLIT>
+// PAIR: two CTAs of a cluster (one TPC) work on 256 tokens with cta_group::2 MMAs (M = 256).  Each CTA keeps its own
+// 128 rows of q / D1 / hidden planes / D2 and loads only HALF of every weight tile (its 64 of the 128 N rows), which
+// halves the L2 -> SM weight stream that bounds the single-CTA kernel.  The leader (cluster rank 0) issues all MMAs;
+// TMA loads of both CTAs are credited to the leader's barriers, commits are multicast to both CTAs, and the epilogue
+// warps of both CTAs arrive on the leader's barriers (see cta_pair.cuh).
+template <int NSPLIT, bool PAIR, bool DBG>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_constant__ CUtensorMap mapA1lo,
                  const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ CUtensorMap mapW1lo,
@@ -95,24 +101,34 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a1 = smem;                                  // [plane][kb] 16 KB tiles
     uint8_t* ring = smem + 8 * kFfnUnit;
-    uint8_t* stage_tiles = ring + kFfnRing * kFfnUnit;
+    constexpr int kPlaneB = PAIR ? kFfnUnit / 2 : kFfnUnit;  // bytes of one plane of a weight tile in THIS CTA's shared memory
+    constexpr int kUnitB = 2 * kPlaneB;                      // ring unit: [hi plane | lo plane] (or the two N halves of the identity)
+    constexpr int kFfnRing = kFfnRingBytes / kUnitB;         // 5 for a pair, 2 for a single CTA
+    constexpr int kNCta = PAIR ? 2 : 1;
+    uint8_t* stage_tiles = ring + kFfnRingBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_tiles + kFfnStageArea);
     uint64_t* a1_full = bars + 0;
     uint64_t* a1_empty = bars + 1;
-    uint64_t* ring_full = bars + 2;                      // [kFfnRing <= 8]
-    uint64_t* ring_empty = bars + 10;                    // [kFfnRing <= 8]
-    uint64_t* d1_full = bars + 18;
-    uint64_t* d1_empty = bars + 19;
-    uint64_t* a2_full = bars + 20;
-    uint64_t* a2_empty = bars + 21;
-    uint64_t* d2_full = bars + 22;
-    uint64_t* d2_empty = bars + 23;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    static_assert(kFfnRing <= 8, "barrier slots");
+    uint64_t* ring_full = bars + 2;                      // [kFfnRing <= 10]
+    uint64_t* ring_empty = bars + 12;                    // [kFfnRing <= 10]
+    uint64_t* d1_full = bars + 22;
+    uint64_t* d1_empty = bars + 23;
+    uint64_t* a2_full = bars + 24;
+    uint64_t* a2_empty = bars + 25;
+    uint64_t* d2_full = bars + 26;
+    uint64_t* d2_empty = bars + 27;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    static_assert(kFfnRing <= 10, "barrier slots");
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tiles = (M + BM - 1) / BM;
+    // tile = BM rows per CTA; a pair takes two consecutive tiles (256 rows) per round
+    const int n_rounds = PAIR ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
+    const int round0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int round_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_of = [&](int r) { return PAIR ? (2 * r + (int)rank) * BM : r * BM; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA1hi); tma_prefetch_desc(&mapW1hi); tma_prefetch_desc(&mapW2hi);
@@ -121,13 +137,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
     if (warp == 1 && lane == 0) {
         mbar_init(a1_full, 1); mbar_init(a1_empty, 1);
         for (int s = 0; s < kFfnRing; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-        mbar_init(d1_full, 1); mbar_init(d1_empty, 16);
-        mbar_init(a2_full, 16); mbar_init(a2_empty, 1);
-        mbar_init(d2_full, 1); mbar_init(d2_empty, 16);
+        mbar_init(d1_full, 1); mbar_init(d1_empty, 16 * kNCta);
+        mbar_init(a2_full, 16 * kNCta); mbar_init(a2_empty, 1);
+        mbar_init(d2_full, 1); mbar_init(d2_empty, 16 * kNCta);
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (PAIR) {                                          // barriers of both CTAs exist before anyone signals them
+        __syncthreads();
+        cluster_sync_all();
+        if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    } else {
+        if (warp == 2) tmem_alloc(tmem_slot, 512);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -138,38 +160,46 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t rphase = 0; uint32_t tphase = 0;
-            auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int bytes_each, int c0, int c1) {
-                // one ring unit: hi tile at the stage base, optional lo tile right behind it
+            auto put = [&](const CUtensorMap* mapa, int ca, const CUtensorMap* mapb, int cb, int c0) {
+                // one ring unit = up to two [128 N rows][64 k] tiles, back to back (a pair member loads its 64 rows of each)
                 mbar_wait(&ring_empty[stage], rphase ^ 1);
-                uint8_t* st = ring + stage * kFfnUnit;
-                mbar_expect_tx(&ring_full[stage], lo ? 2 * bytes_each : bytes_each);
-                tma_load_2d(st, hi, &ring_full[stage], c0, c1);
-                if (lo) tma_load_2d(st + bytes_each, lo, &ring_full[stage], c0, c1);
+                uint8_t* st = ring + stage * kUnitB;
+                const int bytes = (mapb ? 2 : 1) * kPlaneB;
+                if (PAIR) {
+                    if (leader) mbar_expect_tx(&ring_full[stage], 2 * bytes);
+                    tma_load_2d_pair(st, mapa, &ring_full[stage], c0, ca + (int)rank * 64);
+                    if (mapb) tma_load_2d_pair(st + kPlaneB, mapb, &ring_full[stage], c0, cb + (int)rank * 64);
+                } else {
+                    mbar_expect_tx(&ring_full[stage], bytes);
+                    tma_load_2d(st, mapa, &ring_full[stage], c0, ca);
+                    if (mapb) tma_load_2d(st + kPlaneB, mapb, &ring_full[stage], c0, cb);
+                }
                 if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
             };
             auto put_w2 = [&](int cc) {       // W2 columns of hidden chunk cc, per 64-wide K block and output half: hi, lo
                 for (int kb2 = 0; kb2 < 2; ++kb2)
-                    for (int nh = 0; nh < 2; ++nh) {
-                        put(&mapW2hi, nullptr, kFfnUnit, cc * 128 + kb2 * 64, nh * 128);
-                        if (NSPLIT > 1) put(&mapW2lo, nullptr, kFfnUnit, cc * 128 + kb2 * 64, nh * 128);
-                    }
+                    for (int nh = 0; nh < 2; ++nh)
+                        put(&mapW2hi, nh * 128, NSPLIT > 1 ? &mapW2lo : nullptr, nh * 128, cc * 128 + kb2 * 64);
             };
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = tile * BM;
+            for (int r = round0; r < n_rounds; r += round_step) {
+                const int m0 = row_of(r);
                 mbar_wait(a1_empty, tphase ^ 1);
-                mbar_expect_tx(a1_full, kPl * 4 * kFfnUnit);
+                if (!PAIR || leader) mbar_expect_tx(a1_full, kNCta * kPl * 4 * kFfnUnit);
                 for (int kb = 0; kb < 4; ++kb) {
-                    tma_load_2d(a1 + kb * kFfnUnit, &mapA1hi, a1_full, kb * BK, m0);
-                    if (NSPLIT > 1) tma_load_2d(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
+                    if (PAIR) {
+                        tma_load_2d_pair(a1 + kb * kFfnUnit, &mapA1hi, a1_full, kb * BK, m0);
+                        if (NSPLIT > 1) tma_load_2d_pair(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
+                    } else {
+                        tma_load_2d(a1 + kb * kFfnUnit, &mapA1hi, a1_full, kb * BK, m0);
+                        if (NSPLIT > 1) tma_load_2d(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
+                    }
                 }
                 for (int c = 0; c < kChunks; ++c) {
-                    for (int kb = 0; kb < 4; ++kb) {     // W1 rows of hidden chunk c (128 rows), K block kb: hi unit, lo unit
-                        put(&mapW1hi, nullptr, kFfnUnit, kb * BK, c * 128);
-                        if (NSPLIT > 1) put(&mapW1lo, nullptr, kFfnUnit, kb * BK, c * 128);
-                    }
+                    for (int kb = 0; kb < 4; ++kb)       // W1 rows of hidden chunk c (128 rows), K block kb: hi | lo
+                        put(&mapW1hi, c * 128, NSPLIT > 1 ? &mapW1lo : nullptr, c * 128, kb * BK);
                     if (c == kChunks - 1)                // identity block of the augmented W2 (hi plane only): the residual
-                        for (int kb = 0; kb < 4; ++kb)   // is issued right after the last MMA1 (see the MMA warp)
-                            for (int nh = 0; nh < 2; ++nh) put(&mapW2hi, nullptr, kFfnUnit, kFFN + kb * BK, nh * 128);
+                        for (int kb = 0; kb < 4; ++kb)   // is issued right after the last MMA1 (see the MMA warp); unit = both N halves
+                            put(&mapW2hi, 0, &mapW2hi, 128, kFFN + kb * BK);
                     if (c >= 1) put_w2(c - 1);
                 }
                 put_w2(kChunks - 1);
@@ -179,91 +209,96 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp runs the loop; tcgen05 instructions on the elected lane) =====================
-        {
-            constexpr uint32_t idesc128 = make_idesc(BM, 128);
+        if (leader) {
+            constexpr uint32_t idesc128 = make_idesc(kNCta * BM, 128);
+            auto mma_ss = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+                if (PAIR) umma_f16_pair(d, a, b, idesc128, acc); else umma_f16(d, a, b, idesc128, acc);
+            };
+            auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+                if (PAIR) umma_f16_ts_pair(d, a, b, idesc128, acc); else umma_f16_ts(d, a, b, idesc128, acc);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar, 3); else umma_commit(bar); };
+            auto wait = [&](uint64_t* bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
             int stage = 0; uint32_t rphase = 0, tphase = 0;
             uint32_t d1e_phase = 0, a2f_phase = 0, d2e_phase = 0;
             const uint32_t a1_addr = smem_u32(a1);
-            long long tw_ring = 0, tw_d1e = 0, tw_a2f = 0, tw_d2e = 0, tw_a1 = 0, t_all = clock64();
-            // wait for `n` consecutive ring units (n = 1 or 2) and return the address of the first; lo follows hi
-            auto ring_wait = [&](int n, uint32_t& second) -> uint32_t {
-                long long t0 = clock64();
-                mbar_wait(&ring_full[stage], rphase);
-                int s2 = stage + 1; uint32_t ph2 = rphase;
-                if (s2 == kFfnRing) { s2 = 0; ph2 ^= 1; }
-                if (n > 1) mbar_wait(&ring_full[s2], ph2);
+            auto now = [&]() -> long long { return DBG ? clock64() : 0ll; };
+            long long tw_ring = 0, tw_d1e = 0, tw_a2f = 0, tw_d2e = 0, tw_a1 = 0, tw_i1 = 0, tw_i2 = 0, t_all = now();
+            // wait for the next ring unit; returns the address of its first tile, the second follows at +kPlaneB
+            auto ring_wait = [&]() -> uint32_t {
+                long long t0 = now();
+                wait(&ring_full[stage], rphase);
                 tc_fence_after();
-                tw_ring += clock64() - t0;
-                second = smem_u32(ring + s2 * kFfnUnit);
-                return smem_u32(ring + stage * kFfnUnit);
+                tw_ring += now() - t0;
+                return smem_u32(ring + stage * kUnitB);
             };
             auto ring_release = [&]() {
-                if (elect_one()) umma_commit(&ring_empty[stage]);
+                if (elect_one()) commit(&ring_empty[stage]);
                 __syncwarp();
                 if (++stage == kFfnRing) { stage = 0; rphase ^= 1; }
             };
             auto mma2 = [&](int cc) {                    // D2 += hid(cc) * W2[:, cc]^T, hid planes in TMEM
-                { long long t0 = clock64(); mbar_wait(a2_full, a2f_phase); a2f_phase ^= 1; tw_a2f += clock64() - t0; }
+                { long long t0 = now(); wait(a2_full, a2f_phase); a2f_phase ^= 1; tw_a2f += now() - t0; }
                 tc_fence_after();
                 const uint32_t ahi = tA2, alo = tA2 + 64;
                 for (int kb2 = 0; kb2 < 2; ++kb2)
                     for (int nh = 0; nh < 2; ++nh) {
-                        uint32_t ulo;
-                        const uint32_t uhi = ring_wait(NSPLIT > 1 ? 2 : 1, ulo);
-                        const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(ulo);
+                        const uint32_t uhi = ring_wait();
+                        const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(uhi + kPlaneB);
                         const uint32_t d = tD2 + nh * 128;
+                        const long long ti0 = now();
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint32_t acc = (cc | kb2 | k) != 0;
                                 const uint32_t ka = 8 * (kb2 * 4 + k);
                                 if (NSPLIT > 1) {
-                                    umma_f16_ts(d, alo + ka, bhi + 2 * k, idesc128, acc);
-                                    umma_f16_ts(d, ahi + ka, blo + 2 * k, idesc128, 1u);
-                                    umma_f16_ts(d, ahi + ka, bhi + 2 * k, idesc128, 1u);
+                                    mma_ts(d, alo + ka, bhi + 2 * k, acc);
+                                    mma_ts(d, ahi + ka, blo + 2 * k, 1u);
+                                    mma_ts(d, ahi + ka, bhi + 2 * k, 1u);
                                 } else {
-                                    umma_f16_ts(d, ahi + ka, bhi + 2 * k, idesc128, acc);
+                                    mma_ts(d, ahi + ka, bhi + 2 * k, acc);
                                 }
                             }
                         }
                         __syncwarp();
+                        tw_i2 += now() - ti0;
                         ring_release();
-                        if (NSPLIT > 1) ring_release();
                     }
-                if (elect_one()) umma_commit(a2_empty);
+                if (elect_one()) commit(a2_empty);
                 __syncwarp();
             };
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                { long long t0 = clock64(); mbar_wait(a1_full, tphase); tw_a1 += clock64() - t0; }
+            for (int r = round0; r < n_rounds; r += round_step) {
+                { long long t0 = now(); wait(a1_full, tphase); tw_a1 += now() - t0; }
                 tc_fence_after();
                 for (int c = 0; c <= kChunks; ++c) {
                     if (c < kChunks) {                   // D1 = A1 * W1[c]^T   (N = 128)
-                        { long long t0 = clock64(); mbar_wait(d1_empty, d1e_phase ^ 1); d1e_phase ^= 1; tw_d1e += clock64() - t0; }
+                        { long long t0 = now(); wait(d1_empty, d1e_phase ^ 1); d1e_phase ^= 1; tw_d1e += now() - t0; }
                         tc_fence_after();
                         for (int kb = 0; kb < 4; ++kb) {
-                            uint32_t ulo;
-                            const uint32_t uhi = ring_wait(NSPLIT > 1 ? 2 : 1, ulo);
+                            const uint32_t uhi = ring_wait();
                             const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
                             const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
-                            const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(ulo);
+                            const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(uhi + kPlaneB);
+                            const long long ti0 = now();
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const uint32_t acc = (kb | k) != 0;
                                     if (NSPLIT > 1) {
-                                        umma_f16(tD1, alo + 2 * k, bhi + 2 * k, idesc128, acc);
-                                        umma_f16(tD1, ahi + 2 * k, blo + 2 * k, idesc128, 1u);
-                                        umma_f16(tD1, ahi + 2 * k, bhi + 2 * k, idesc128, 1u);
+                                        mma_ss(tD1, alo + 2 * k, bhi + 2 * k, acc);
+                                        mma_ss(tD1, ahi + 2 * k, blo + 2 * k, 1u);
+                                        mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, 1u);
                                     } else {
-                                        umma_f16(tD1, ahi + 2 * k, bhi + 2 * k, idesc128, acc);
+                                        mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, acc);
                                     }
                                 }
                             }
                             __syncwarp();
+                            tw_i1 += now() - ti0;
                             ring_release();
-                            if (NSPLIT > 1) ring_release();
                         }
-                        if (elect_one()) umma_commit(d1_full);
+                        if (elect_one()) commit(d1_full);
                         __syncwarp();
                     }
                     if (c == kChunks - 1) {              // last MMA1 issued: add the residual now and release q's planes early
@@ -271,43 +306,46 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                     for (int kb = 0; kb < 4; ++kb) {
                         const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
                         const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
-                        for (int nh = 0; nh < 2; ++nh) {
-                            uint32_t dummy;
-                            const uint64_t bi = make_smem_desc(ring_wait(1, dummy));
-                            const uint32_t d = tD2 + nh * 128;
-                            if (elect_one()) {
-    #pragma unroll
+                        const uint32_t ui = ring_wait();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int nh = 0; nh < 2; ++nh) {
+                                const uint64_t bi = make_smem_desc(ui + nh * kPlaneB);
+                                const uint32_t d = tD2 + nh * 128;
+#pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    if (NSPLIT > 1) umma_f16(d, alo + 2 * k, bi + 2 * k, idesc128, 1u);
-                                    umma_f16(d, ahi + 2 * k, bi + 2 * k, idesc128, 1u);
+                                    if (NSPLIT > 1) mma_ss(d, alo + 2 * k, bi + 2 * k, 1u);
+                                    mma_ss(d, ahi + 2 * k, bi + 2 * k, 1u);
                                 }
                             }
-                            __syncwarp();
-                            ring_release();
                         }
+                        __syncwarp();
+                        ring_release();
                     }
-                        if (elect_one()) umma_commit(a1_empty);   // q planes may be overwritten by the next tile's load
+                        if (elect_one()) commit(a1_empty);   // q planes may be overwritten by the next tile's load
                         __syncwarp();
                     }
                     if (c >= 1) {
                         if (c == 1) {                    // D2 of the previous tile must have been drained
-                            { long long t0 = clock64(); mbar_wait(d2_empty, d2e_phase ^ 1); d2e_phase ^= 1; tw_d2e += clock64() - t0; }
+                            { long long t0 = now(); wait(d2_empty, d2e_phase ^ 1); d2e_phase ^= 1; tw_d2e += now() - t0; }
                             tc_fence_after();
                         }
                         mma2(c - 1);
                     }
                 }
-                if (elect_one()) umma_commit(d2_full);
+                if (elect_one()) commit(d2_full);
                 __syncwarp();
                 tphase ^= 1;
             }
-            if (p.dbg && lane == 0) {
-                atomicAdd(&p.dbg[0], (unsigned long long)(clock64() - t_all));
+            if (DBG && p.dbg && lane == 0) {
+                atomicAdd(&p.dbg[0], (unsigned long long)(now() - t_all));
                 atomicAdd(&p.dbg[1], (unsigned long long)tw_ring);
                 atomicAdd(&p.dbg[2], (unsigned long long)tw_d1e);
                 atomicAdd(&p.dbg[3], (unsigned long long)tw_a2f);
                 atomicAdd(&p.dbg[4], (unsigned long long)tw_d2e);
                 atomicAdd(&p.dbg[5], (unsigned long long)tw_a1);
+                atomicAdd(&p.dbg[6], (unsigned long long)tw_i1);
+                atomicAdd(&p.dbg[7], (unsigned long long)tw_i2);
             }
         }
         __syncwarp();
@@ -320,8 +358,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         uint32_t d1f_phase = 0, a2e_phase = 0;
         uint32_t d2f_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m0 = tile * BM;
+        auto arrive = [&](uint64_t* bar) { if (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar); };
+        for (int r = round0; r < n_rounds; r += round_step) {
+            const int m0 = row_of(r);
             const int wrow0 = m0 + q * 32;
             const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
             // ---- per hidden chunk: GELU of this warp's 32 columns, planes back into TMEM ----
@@ -333,7 +372,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 tmem_ld32(tD1 + part * 32 + lane_sel, v);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d1_empty);                // D1 may be overwritten by MMA1 of chunk c + 1
+                if (lane == 0) arrive(d1_empty);                // D1 may be overwritten by MMA1 of chunk c + 1
                 uint32_t hi[16], lo[16];
                 const float* bp = p.b1 + c * 128 + part * 32;
 #pragma unroll
@@ -379,7 +418,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a2_full);
+                if (lane == 0) arrive(a2_full);
             }
             // ---- final: LayerNorm (+ folded FiLM) of this warp's 64 columns of D2 ----
             mbar_wait(d2_full, d2f_phase); d2f_phase ^= 1;
@@ -472,33 +511,57 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(d2_empty);
+            if (lane == 0) arrive(d2_empty);
             named_bar_sync(1 + q, 128);                  // partners may reuse this warp's tile for the next tile's partials
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                        // the peer may still read this CTA's shared / tensor memory
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
-template <int NSPLIT>
-inline cudaError_t launch_ffn_fused(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
+template <int NSPLIT, bool PAIR, bool DBG>
+inline cudaError_t launch_ffn_fused_(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
                                     const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
                                     const FfnParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = ffn_fused_kernel<NSPLIT>;
+    auto kern = ffn_fused_kernel<NSPLIT, PAIR, DBG>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int n_tiles = (M + BM - 1) / BM;
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    kern<<<grid, kFfnThreads, kFfnSmem, st>>>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
-    return cudaSuccess;
+    if (!PAIR) {
+        const int n_tiles = (M + BM - 1) / BM;
+        const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+        kern<<<grid, kFfnThreads, kFfnSmem, st>>>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
+        return cudaGetLastError();
+    }
+    const int n_rounds = (M + 2 * BM - 1) / (2 * BM);
+    const int pairs = n_rounds < num_sms / 2 ? n_rounds : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kFfnThreads);
+    cfg.dynamicSmemBytes = kFfnSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
+}
+
+template <int NSPLIT, bool PAIR>
+inline cudaError_t launch_ffn_fused(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
+                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
+                                    const FfnParams& p, int num_sms, cudaStream_t st) {
+    return p.dbg ? launch_ffn_fused_<NSPLIT, PAIR, true>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p, num_sms, st)
+                 : launch_ffn_fused_<NSPLIT, PAIR, false>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p, num_sms, st);
 }
 
 }  // namespace tc
