@@ -16,7 +16,6 @@
 // four warps per TMEM lane quarter).  MMA1 of chunk c+1 overlaps the GELU epilogue and MMA2 of chunk c.
 #pragma once
 #include "gemm_tc.cuh"
-#include "cta_pair.cuh"
 
 namespace ddp {
 namespace tc {
@@ -50,45 +49,17 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : TMEM_R16(r, 0)
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
 
-// 32 rows x 32 bytes through a 1 KB tile: `h` = the row's 32 bytes as 2 uint4; dst / ld in halves
-__device__ __forceinline__ void stage_store_32b(float* stg, const uint4* h, __half* dst, int ld, int rows_valid, int lane) {
-    uint4* s16 = reinterpret_cast<uint4*>(stg);
-    s16[lane * 2 + (0 ^ ((lane >> 2) & 1))] = h[0];
-    s16[lane * 2 + (1 ^ ((lane >> 2) & 1))] = h[1];
-    __syncwarp();
-    const int c = lane & 1;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int r = (lane >> 1) + 16 * i;
-        uint4 x = s16[r * 2 + (c ^ ((r >> 2) & 1))];
-        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c * 8) = x;
-    }
-    __syncwarp();
-}
-
 // PAIR: two CTAs of a cluster (one TPC) work on 256 tokens with cta_group::2 MMAs (M = 256).  Each CTA keeps its own
 // 128 rows of q / D1 / hidden planes / D2 and loads only HALF of every weight tile (its 64 of the 128 N rows), which
 // halves the L2 -> SM weight stream that bounds the single-CTA kernel.  The leader (cluster rank 0) issues all MMAs;
 // TMA loads of both CTAs are credited to the leader's barriers, commits are multicast to both CTAs, and the epilogue
-// warps of both CTAs arrive on the leader's barriers (see cta_pair.cuh).
+// warps of both CTAs arrive on the leader's barriers (CTA-pair wrappers in gemm_tc.cuh).
 template <int NSPLIT, bool PAIR, bool DBG>
 __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_constant__ CUtensorMap mapA1lo,

@@ -74,6 +74,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// pull one box of a tensor into L2 (no shared-memory destination): hides the HBM latency of a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -108,6 +113,87 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) wrappers: two CTAs of a cluster on one TPC run one M = 256 MMA, each holding its 128 rows
+// of A / D and half of the B tile.  The leader (cluster rank 0) issues the MMAs; TMA loads of both CTAs report to
+// the leader's mbarrier; tcgen05.commit multicasts its arrival to the same barrier in both CTAs.
+// (functional check: tools/ubench_2cta.cu)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s counterpart in the leader CTA (bit 24 of a shared-window address is the CTA's
+// rank inside its pair; clearing it selects rank 0)
+__device__ __forceinline__ uint32_t leader_smem_u32(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+
+// TMA load into this CTA's shared memory; the bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive (release, cluster scope) on the leader's copy of `bar`
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
+}
+// cluster-scope acquire wait on this CTA's own barrier (pairs with arrivals from the peer CTA)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 28)) __trap();
+    }
+}
+
+// executed by the same warp index in BOTH CTAs
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[2 x 128 lanes] (+)= A * B^T with M = 256: descriptors / TMEM addresses are the leader's, the peer uses the same offsets
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on `bar` (same offset) in every CTA of `mask` once all earlier MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask = 3) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 
 // 32 lanes x 64 columns of fp32: thread t of the warp gets lane (lane_base + t), columns col..col+63
 #define TMEM_R16(r, o) "=r"(r[o+0]), "=r"(r[o+1]), "=r"(r[o+2]), "=r"(r[o+3]), "=r"(r[o+4]), "=r"(r[o+5]), "=r"(r[o+6]), "=r"(r[o+7]), \
@@ -258,6 +344,46 @@ __device__ __forceinline__ void split_store64(float* stg, const float (&v)[64], 
 
 enum { EPI_BIAS = 0, EPI_ADD_COND = 1, EPI_SAMPLING = 2, EPI_GELU = 3, EPI_RES_LN = 4 };
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : TMEM_R16(r, 0)
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 rows x 32 bytes through a 1 KB tile: `h` = the row's 32 bytes as 2 uint4; dst / ld in halves
+__device__ __forceinline__ void stage_store_32b(float* stg, const uint4* h, __half* dst, int ld, int rows_valid, int lane) {
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+    s16[lane * 2 + (0 ^ ((lane >> 2) & 1))] = h[0];
+    s16[lane * 2 + (1 ^ ((lane >> 2) & 1))] = h[1];
+    __syncwarp();
+    const int c = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int r = (lane >> 1) + 16 * i;
+        uint4 x = s16[r * 2 + (c ^ ((r >> 2) & 1))];
+        if (r < rows_valid) *reinterpret_cast<uint4*>(dst + (size_t)r * ld + c * 8) = x;
+    }
+    __syncwarp();
+}
+
 struct EpiParams {
     float scale;             // undoes the operand scales: acc * scale = A*W^T
     const float* bias;       // [N] or null
@@ -282,28 +408,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageAreaBytes = 32768;       // store staging tiles of all epilogue warps
-__host__ __device__ constexpr int epi_warps(int epi) { return epi == EPI_GELU ? 16 : 8; }    // the GELU epilogue is issue-bound: 16 warps
+__host__ __device__ constexpr int epi_warps(int epi) { return (epi == EPI_GELU || epi == EPI_SAMPLING) ? 16 : 8; }    // issue-bound epilogues: 16 warps
 __host__ __device__ constexpr int tc_threads(int epi) { return 32 * (2 + epi_warps(epi)); }
 
-template <int BN, int NSPLIT, int EPI = EPI_BIAS>
+// PAIR: the kernel runs on CTA pairs (cluster of 2): M = 256 per MMA, each CTA stages its 128 rows of A and HALF of the
+// B tile (its BN / 2 rows), so the L2 -> SM stream of weight tiles per token halves.
+template <int BN, int NSPLIT, int EPI = EPI_BIAS, bool PAIR = false>
 struct Cfg {
     static constexpr int kEpiWarps = epi_warps(EPI);
     static constexpr int kStageTileBytes = kStageAreaBytes / kEpiWarps;
     static constexpr int kABytes = BM * BK * 2;               // one fp16 plane of an A stage
-    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kBRows = PAIR ? BN / 2 : BN;         // B rows staged by THIS CTA
+    static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = NSPLIT == 1 ? (kABytes + kBBytes) : 2 * (kABytes + kBBytes);
     static constexpr int kStages = (192 * 1024 / kStageBytes) > 6 ? 6 : (192 * 1024 / kStageBytes);
     static constexpr int kTmemCols = 2 * BN <= 32 ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-    static constexpr int kEpiActive = EPI == EPI_GELU ? 16 : (BN >= 128 ? 8 : 4);      // epilogue warps that take part
-    static constexpr int kColsPerWarp = EPI == EPI_GELU ? BN / 4 : (BN >= 128 ? BN / 2 : BN);
+    static constexpr int kEpiActive = (EPI == EPI_GELU || EPI == EPI_SAMPLING) ? 16 : (BN >= 128 ? 8 : 4);      // epilogue warps that take part
+    static constexpr int kColsPerWarp = (EPI == EPI_GELU || EPI == EPI_SAMPLING) ? BN / 4 : (BN >= 128 ? BN / 2 : BN);
     static constexpr int kSmemBytes = kStages * kStageBytes + kStageAreaBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(EPI != EPI_GELU || BN == 256, "the 16-warp GELU epilogue assumes 64 columns per warp");
     static_assert(kStages >= 2, "need at least two stages");
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
+    static_assert(!PAIR || kBBytes % 1024 == 0, "a pair member's B half must keep the 1024-byte swizzle alignment");
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared memory of sm_100");
 };
 
-template <int BN, int NSPLIT, int EPI>
+template <int BN, int NSPLIT, int EPI, bool PAIR>
 __global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapA2hi, const __grid_constant__ CUtensorMap mapA2lo,
@@ -311,8 +441,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                int M, int K, int K1, int n_tiles_n, EpiParams ep) {
     // A is the K-concatenation [A (K1 columns) | A2 (K - K1 columns)]: the residual of a post-norm block rides
     // along as extra K against a scaled identity block of W, so the epilogue never reads it from global memory.
-    using C = Cfg<BN, NSPLIT, EPI>;
+    using C = Cfg<BN, NSPLIT, EPI, PAIR>;
     constexpr int kStageTileBytes = C::kStageTileBytes;
+    constexpr int kNCta = PAIR ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (128B swizzle) by pointer arithmetic on the shared array, so that the compiler keeps
     // the shared address space (LDS/STS instead of generic accesses) for the staging tiles
@@ -328,7 +459,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles_m = (M + BM - 1) / BM;
-    const int n_tiles = n_tiles_m * n_tiles_n;
+    // a "tile" below is one round of work of this CTA: BM rows x BN columns; a pair takes two consecutive row tiles
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int n_tiles = (PAIR ? (n_tiles_m + 1) / 2 : n_tiles_m) * n_tiles_n;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_of = [&](int tile) { return PAIR ? (2 * (tile / n_tiles_n) + (int)rank) * BM : (tile / n_tiles_n) * BM; };
     const int n_kb = K / BK;
     const int n_kb1 = K1 / BK;
 
@@ -339,11 +476,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], C::kEpiActive); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], C::kEpiActive * kNCta); }
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+    if (PAIR) {                                          // barriers of both CTAs exist before anyone signals them
+        __syncthreads();
+        cluster_sync_all();
+        if (warp == 2) tmem_alloc_pair(tmem_slot, C::kTmemCols);
+    } else {
+        if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -353,20 +496,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles_n) * BM;
-                const int n0 = (tile % n_tiles_n) * BN;
+            auto load = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                if (PAIR) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+            };
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                const int m0 = row_of(tile);
+                const int n0 = (tile % n_tiles_n) * BN + (int)rank * C::kBRows;      // a pair member stages its half of the B rows
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* st = smem + stage * C::kStageBytes;
-                    mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+                    if (leader) mbar_expect_tx(&full_bar[stage], kNCta * C::kStageBytes);   // bytes of both CTAs land on the leader's barrier
                     const bool second = kb >= n_kb1;
                     const int ka = (second ? kb - n_kb1 : kb) * BK;
-                    tma_load_2d(st, second ? &mapA2hi : &mapAhi, &full_bar[stage], ka, m0);
-                    tma_load_2d(st + C::kABytes, &mapBhi, &full_bar[stage], kb * BK, n0);
+                    load(st, second ? &mapA2hi : &mapAhi, &full_bar[stage], ka, m0);
+                    load(st + C::kABytes, &mapBhi, &full_bar[stage], kb * BK, n0);
                     if (NSPLIT > 1) {
-                        tma_load_2d(st + C::kABytes + C::kBBytes, second ? &mapA2lo : &mapAlo, &full_bar[stage], ka, m0);
-                        tma_load_2d(st + 2 * C::kABytes + C::kBBytes, &mapBlo, &full_bar[stage], kb * BK, n0);
+                        load(st + C::kABytes + C::kBBytes, second ? &mapA2lo : &mapAlo, &full_bar[stage], ka, m0);
+                        load(st + 2 * C::kABytes + C::kBBytes, &mapBlo, &full_bar[stage], kb * BK, n0);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -374,17 +520,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
+        // ===================== MMA issuer (the leader's, for a pair) =====================
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(kNCta * BM, BN);
+            auto umma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
+                if (PAIR) umma_f16_pair(d, a, b, idesc, accum); else umma_f16(d, a, b, idesc, accum);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_pair(bar, 3); else umma_commit(bar); };
+            auto wait = [&](uint64_t* bar, uint32_t parity) { if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < n_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
                     const uint64_t a_hi = make_smem_desc(st);
@@ -397,17 +548,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         const uint32_t accum = (kb | k) != 0;
                         if (elect_one()) {
                             if (NSPLIT > 1) {
-                                umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, accum);    // small terms first
-                                umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                                umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                                umma(d_tmem, a_lo + koff, b_hi + koff, accum);    // small terms first
+                                umma(d_tmem, a_hi + koff, b_lo + koff, 1u);
+                                umma(d_tmem, a_hi + koff, b_hi + koff, 1u);
                             } else {
-                                umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, accum);
+                                umma(d_tmem, a_hi + koff, b_hi + koff, accum);
                             }
                         }
                     }
                     if (elect_one()) {
-                        umma_commit(&empty_bar[stage]);                 // stage free once these MMAs retire
-                        if (kb == n_kb - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
+                        commit(&empty_bar[stage]);                 // stage free once these MMAs retire
+                        if (kb == n_kb - 1) commit(&tfull_bar[acc]);   // accumulator complete
                     }
                     __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -424,8 +575,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
         const int cbeg = half * C::kColsPerWarp;
         float* stg = reinterpret_cast<float*>(stage_tiles + ew * kStageTileBytes);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles_n) * BM;
+        for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+            const int m0 = row_of(tile);
             const int n0 = (tile % n_tiles_n) * BN;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
@@ -545,6 +696,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     if (NSPLIT > 1)
                         stage_store_f16_32(stg, lo, ep.split.lo + (size_t)wrow0 * ep.split.ld + col0, ep.split.ld, rows_valid, lane);
                 }
+            } else if (EPI == EPI_SAMPLING) {
+                // accumulator columns: 0..63 = (x, y) offsets of 32 sampling points (head, point), 64..95 attention logits,
+                // 96..127 padding.  Four warps per lane quarter: warp `half` (0..3) owns heads 2*half and 2*half + 1, i.e.
+                // offset columns [16 half, +16) and logits [64 + 8 half, +8); it writes the matching 32-byte pieces of the
+                // four record sections (index words, fx, fy, attention weights).
+                const int n = (int)(srow % ep.N_tok);
+                __half* rech = reinterpret_cast<__half*>(ep.rec + (size_t)wrow0 * kRecW);       // 2 halves per record word
+                const float* pp = ep.pew + (size_t)n * kSampW;
+                float o[16], a[8];
+                tmem_ld16(t_row + 16 * half, o);
+                tmem_ld8(t_row + 64 + 8 * half, a);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(pp + 16 * half + i * 4);
+                    o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
+                    o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4);
+                    a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
+                    a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
+                }
+                if (ep.out) {                       // raw offsets for the test tap (fp32, 2 x 8 columns)
+                    __half* oh = reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 16 * half);
+                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[0]), oh, 2 * ep.ldc, rows_valid, lane);
+                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[8]), oh + 16, 2 * ep.ldc, rows_valid, lane);
+                }
+                {
+                    const int ti = n / ep.W, tj = n - ti * ep.W;
+                    const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
+                    const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
+                    uint4 widx[2], wfx[2], wfy[2];
+                    uint32_t* wi = reinterpret_cast<uint32_t*>(widx);
+                    float* fxp = reinterpret_cast<float*>(wfx);
+                    float* fyp = reinterpret_cast<float*>(wfy);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
+                    stage_store_32b(stg, widx, rech + 2 * (8 * half), 2 * kRecW, rows_valid, lane);
+                    stage_store_32b(stg, wfx, rech + 2 * (32 + 8 * half), 2 * kRecW, rows_valid, lane);
+                    stage_store_32b(stg, wfy, rech + 2 * (64 + 8 * half), 2 * kRecW, rows_valid, lane);
+                }
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {       // softmax over each head's 4 points
+                    const float mx = fmaxf(fmaxf(a[g * 4], a[g * 4 + 1]), fmaxf(a[g * 4 + 2], a[g * 4 + 3]));
+                    const float e0 = expf(a[g * 4] - mx), e1 = expf(a[g * 4 + 1] - mx), e2 = expf(a[g * 4 + 2] - mx), e3 = expf(a[g * 4 + 3] - mx);
+                    const float sden = (e0 + e1) + (e2 + e3);
+                    a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
+                }
+                stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]), rech + 2 * (96 + 8 * half), 2 * kRecW, rows_valid, lane);
+                if (ep.out)
+                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]),
+                                    reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 64 + 8 * half), 2 * ep.ldc, rows_valid, lane);
             } else {
 #pragma unroll 1
                 for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {
@@ -563,60 +768,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                             v[i * 4 + 0] = fmaf(v[i * 4 + 0], ep.scale, c4.x); v[i * 4 + 1] = fmaf(v[i * 4 + 1], ep.scale, c4.y);
                             v[i * 4 + 2] = fmaf(v[i * 4 + 2], ep.scale, c4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], ep.scale, c4.w);
                         }
-                    } else if (EPI == EPI_SAMPLING) {
-                        // accumulator columns: 0..63 = (x, y) offsets of 32 sampling points, 64..95 attention logits, 96..127 padding.
-                        // Any warp of a lane quarter may read any column, so the two warps of a quarter split the points:
-                        // warp `half` resolves points 16*half .. 16*half+15 (columns 32*half .. +31); half 1 also owns the
-                        // attention weights.  (v[] was loaded from columns cbeg.. = 64*half..; reload what this warp needs.)
-                        const int n = (int)(srow % ep.N_tok);
-                        float* recf = reinterpret_cast<float*>(ep.rec + (size_t)wrow0 * kRecW);
-                        const float* pp = ep.pew + (size_t)n * kSampW;
-                        float o[32];
-                        tmem_ld32(t_row + 32 * half, o);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 p4 = *reinterpret_cast<const float4*>(pp + 32 * half + i * 4);
-                            o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
-                            o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
-                        }
-                        if (ep.out) stage_store_f32(stg, o, ep.out + (size_t)wrow0 * ep.ldc + 32 * half, ep.ldc, rows_valid, lane);
-                        {
-                            const int ti = n / ep.W, tj = n - ti * ep.W;
-                            const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
-                            const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
-                            uint4 widx[4], wfx[4], wfy[4];
-                            uint32_t* wi = reinterpret_cast<uint32_t*>(widx);
-                            float* fxp = reinterpret_cast<float*>(wfx);
-                            float* fyp = reinterpret_cast<float*>(wfy);
-#pragma unroll
-                            for (int k = 0; k < 16; ++k)
-                                msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
-                            // 16 words = 64-byte rows: same tile geometry as 32 fp16 columns
-                            __half* rech = reinterpret_cast<__half*>(recf);
-                            stage_store_f16_32(stg, widx, rech + 2 * (16 * half), 2 * kRecW, rows_valid, lane);
-                            stage_store_f16_32(stg, wfx, rech + 2 * (32 + 16 * half), 2 * kRecW, rows_valid, lane);
-                            stage_store_f16_32(stg, wfy, rech + 2 * (64 + 16 * half), 2 * kRecW, rows_valid, lane);
-                        }
-                        if (half == 1) {            // attention weights: softmax over each head's 4 points (columns 64..95)
-                            float a[32];
-                            tmem_ld32(t_row + 64, a);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + i * 4);
-                                a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
-                                a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
-                            }
-#pragma unroll
-                            for (int g = 0; g < 8; ++g) {
-                                const float mx = fmaxf(fmaxf(a[g * 4], a[g * 4 + 1]), fmaxf(a[g * 4 + 2], a[g * 4 + 3]));
-                                const float e0 = expf(a[g * 4] - mx), e1 = expf(a[g * 4 + 1] - mx), e2 = expf(a[g * 4 + 2] - mx), e3 = expf(a[g * 4 + 3] - mx);
-                                const float sden = (e0 + e1) + (e2 + e3);
-                                a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
-                            }
-                            stage_store_f32(stg, a, recf + 96, kRecW, rows_valid, lane);
-                            if (ep.out) stage_store_f32(stg, a, ep.out + (size_t)wrow0 * ep.ldc + 64, ep.ldc, rows_valid, lane);
-                        }
-                        continue;       // everything stored above
                     } else {
 #pragma unroll
                         for (int i = 0; i < W / 4; ++i) {
@@ -647,15 +798,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             // accumulator drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();                        // the peer may still read this CTA's shared / tensor memory
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::kTmemCols);
+        if (PAIR) tmem_dealloc_pair(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
 
@@ -691,23 +843,40 @@ inline bool make_map_f16(CUtensorMap* map, const void* base, uint64_t rows, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int NSPLIT, int EPI>
+template <int BN, int NSPLIT, int EPI, bool PAIR = false>
 inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& a2Hi,
                                   const CUtensorMap& a2Lo, const CUtensorMap& bHi, const CUtensorMap& bLo, int M, int K,
                                   int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st) {
-    using C = Cfg<BN, NSPLIT, EPI>;
+    // PAIR: bHi / bLo must be maps with BN / 2-row boxes
+    using C = Cfg<BN, NSPLIT, EPI, PAIR>;
     static bool attr_set = false;
-    auto kern = gemm_tc_kernel<BN, NSPLIT, EPI>;
+    auto kern = gemm_tc_kernel<BN, NSPLIT, EPI, PAIR>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int n_tiles_n = n_cols_padded / BN;
-    const int n_tiles = ((M + BM - 1) / BM) * n_tiles_n;
-    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    kern<<<grid, tc_threads(EPI), C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
-    return cudaSuccess;
+    const int n_tiles_m = (M + BM - 1) / BM;
+    if (!PAIR) {
+        const int n_tiles = n_tiles_m * n_tiles_n;
+        const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+        kern<<<grid, tc_threads(EPI), C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
+        return cudaSuccess;
+    }
+    const int n_rounds = ((n_tiles_m + 1) / 2) * n_tiles_n;
+    const int pairs = n_rounds < num_sms / 2 ? n_rounds : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(tc_threads(EPI));
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
 }
 
 }  // namespace tc

@@ -1,4 +1,4 @@
-// Functional check of the CTA-pair primitives in ddp_b200/csrc/cta_pair.cuh on one cluster:
+// Functional check of the CTA-pair primitives in ddp_b200/csrc/gemm_tc.cuh on one cluster:
 //   D  = A * B^T   (A [256 x 64], B [128 x 64], fp16, M = 256 across two CTAs), operands from shared memory (SS)
 //   D2 = A * B^T   with A re-staged in tensor memory by the epilogue warps of both CTAs (TS) after a remote arrive
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ubench_2cta tools/ubench_2cta.cu -lcuda
@@ -9,7 +9,6 @@
 #include "../ddp_b200/csrc/common.cuh"
 #include "../ddp_b200/csrc/gemm_tc.cuh"
 #include "../ddp_b200/csrc/ffn_fused.cuh"
-#include "../ddp_b200/csrc/cta_pair.cuh"
 using namespace ddp;
 using namespace ddp::tc;
 
