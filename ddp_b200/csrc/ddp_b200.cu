@@ -72,7 +72,7 @@ struct ddp_handle {
     // tcgen05 path (gemm_mode != FP32)
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
-    bool gemm_pair = false;     // value / sampling / output projections on CTA pairs (DDP_B200_GEMM_PAIR=1)
+    int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
     unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
     int nsplit = 1;
@@ -320,9 +320,9 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
     TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, aMaps, (W).K, W, M_, ncols_pad, ep)
 
 // same GEMM on CTA pairs (cta_group::2) when the handle enables them: each CTA streams half of every weight tile
-#define TC_GEMM2P(h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep)                                     \
+#define TC_GEMM2P(bit, h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep)                                \
     do {                                                                                                              \
-        if (!(h)->gemm_pair) { TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep); break; }    \
+        if (!((h)->gemm_pair & (bit))) { TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep); break; }    \
         prof_begin(h, tag, st);                                                                                       \
         cudaError_t e_ = (h)->nsplit == 3                                                                             \
             ? tc::launch_gemm_tc<BN_, 3, EPI_, true>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_pair_hi, (W).map_pair_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st) \
@@ -331,8 +331,8 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
         if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "tcgen05 pair gemm setup failed: %s", cudaGetErrorString(e_)); \
         LAUNCH_CHECK(h);                                                                                              \
     } while (0)
-#define TC_GEMMP(h, tag, st, BN_, EPI_, aMaps, W, M_, ncols_pad, ep) \
-    TC_GEMM2P(h, tag, st, BN_, EPI_, aMaps, aMaps, (W).K, W, M_, ncols_pad, ep)
+#define TC_GEMMP(bit, h, tag, st, BN_, EPI_, aMaps, W, M_, ncols_pad, ep) \
+    TC_GEMM2P(bit, h, tag, st, BN_, EPI_, aMaps, aMaps, (W).K, W, M_, ncols_pad, ep)
 
 int repack(ddp_handle* h, const float* src, int rows, int K, int row_stride, int k_stride, int off,
            float* dst, int ld, int col0, cudaStream_t st) {
@@ -595,7 +595,7 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* e = getenv("DDP_B200_FUSE_FFN");
         h->fuse_ffn = h->tc && (e == nullptr || atoi(e) != 0);
         const char* ge = getenv("DDP_B200_GEMM_PAIR");
-        h->gemm_pair = h->tc && ge != nullptr && atoi(ge) != 0;
+        h->gemm_pair = (h->tc && ge != nullptr) ? atoi(ge) : 0;
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         const char* d = getenv("DDP_B200_FFN_DBG");
@@ -878,7 +878,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
             {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
                 tc::EpiParams ep{};
                 ep.scale = T.v.inv_scale; ep.bias = L.bv; ep.out = ws.V; ep.ldc = kE; ep.ncols = kE;
-                TC_GEMMP(h, DDP_K_VALUE, st, 256, tc::EPI_BIAS, h->mA_q, T.v, M, kE, ep);
+                TC_GEMMP(1, h, DDP_K_VALUE, st, 256, tc::EPI_BIAS, h->mA_q, T.v, M, kE, ep);
             }
             {   // offsets / attention weights = proj(q + pos) = q W^T + pew
                 tc::EpiParams ep{};
@@ -886,7 +886,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
                 ep.scale = T.s.inv_scale; ep.out = want_s ? ws.samp : nullptr; ep.ldc = kSampW; ep.ncols = kSampW;
                 ep.pew = h->pew[j]; ep.N_tok = N; ep.rec = ws.rec; ep.H = h->H; ep.W = h->W;
-                TC_GEMMP(h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
+                TC_GEMMP(2, h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
             }
             if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
             if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;   // written only when tapped
@@ -901,7 +901,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = has_tap(h, DDP_TAP_LN1, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
                 ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                 ep.ln_g = L.g1; ep.ln_b = L.e1;
-                TC_GEMM2P(h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
+                TC_GEMM2P(4, h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
             }
             if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
             if (h->fuse_ffn) {   // q = FiLM(LN2(q + W2 gelu(W1 q + b1) + b2)) in ONE kernel, hidden activation kept in TMEM

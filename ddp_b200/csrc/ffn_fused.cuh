@@ -499,12 +499,16 @@ template <int NSPLIT, bool PAIR, bool DBG>
 inline cudaError_t launch_ffn_fused_(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
                                     const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
                                     const FfnParams& p, int num_sms, cudaStream_t st) {
-    static bool attr_set = false;
     auto kern = ffn_fused_kernel<NSPLIT, PAIR, DBG>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    {   // per-device attribute
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     if (!PAIR) {
         const int n_tiles = (M + BM - 1) / BM;

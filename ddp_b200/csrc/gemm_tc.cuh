@@ -849,12 +849,16 @@ inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo
                                   int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st) {
     // PAIR: bHi / bLo must be maps with BN / 2-row boxes
     using C = Cfg<BN, NSPLIT, EPI, PAIR>;
-    static bool attr_set = false;
     auto kern = gemm_tc_kernel<BN, NSPLIT, EPI, PAIR>;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+    {   // the attribute is per device: remember it per device ordinal (one handle per GPU, but several GPUs per process are legal)
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
     }
     const int n_tiles_n = n_cols_padded / BN;
     const int n_tiles_m = (M + BM - 1) / BM;

@@ -439,6 +439,23 @@ def test_unfused_ffn_pair_still_correct(monkeypatch):
     check_seg_output(out, ref, "unfused FFN pair")
 
 
+@pytest.mark.parametrize("env", [{"DDP_B200_FFN_PAIR": "0"}, {"DDP_B200_GEMM_PAIR": "7"},
+                                 {"DDP_B200_FFN_PAIR": "0", "DDP_B200_GEMM_PAIR": "7"}],
+                         ids=["ffn_single_cta", "gemm_pairs", "ffn_single_gemm_pairs"])
+def test_cta_pair_options_agree_with_oracle(monkeypatch, env):
+    """The fused FFN runs on CTA pairs (cta_group::2) by default and the projections on single CTAs; the other
+    combinations (DDP_B200_FFN_PAIR=0, DDP_B200_GEMM_PAIR bit mask) must give the same answer.  The ragged grid
+    (9 x 15 tokens, 2 images: 270 rows = 3 row tiles) leaves the second CTA of the last pair without rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    W = O.make_weights(cfg, seed=35)
+    x, noise = O.make_inputs(cfg, 2, 9, 15, seed=82)
+    ref = O.sample(W, cfg, x, noise)
+    out = make_engine(cfg, W, "tc_3xf16").sample(x.cuda(), noise.cuda()).cpu()
+    check_seg_output(out, ref, f"pair options {env}")
+
+
 def test_full_size_single_step_against_oracle():
     """BASELINE config-3 token grid (128 x 256 = 32768 tokens, 19 classes), one image, one DDIM step: the whole
     per-step path at full size against the oracle (about 10-20 s of CPU work)."""
