@@ -595,7 +595,7 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* e = getenv("DDP_B200_FUSE_FFN");
         h->fuse_ffn = h->tc && (e == nullptr || atoi(e) != 0);
         const char* ge = getenv("DDP_B200_GEMM_PAIR");
-        h->gemm_pair = (h->tc && ge != nullptr) ? atoi(ge) : 0;
+        h->gemm_pair = !h->tc ? 0 : (ge != nullptr ? atoi(ge) : 4);     // default: output projection on pairs (12.6 -> 11.3 ms / sample)
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         const char* d = getenv("DDP_B200_FFN_DBG");

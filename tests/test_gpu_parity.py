@@ -440,11 +440,11 @@ def test_unfused_ffn_pair_still_correct(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"DDP_B200_FFN_PAIR": "0"}, {"DDP_B200_GEMM_PAIR": "7"},
-                                 {"DDP_B200_FFN_PAIR": "0", "DDP_B200_GEMM_PAIR": "7"}],
-                         ids=["ffn_single_cta", "gemm_pairs", "ffn_single_gemm_pairs"])
+                                 {"DDP_B200_FFN_PAIR": "0", "DDP_B200_GEMM_PAIR": "0"}],
+                         ids=["ffn_single_cta", "all_gemm_pairs", "no_pairs"])
 def test_cta_pair_options_agree_with_oracle(monkeypatch, env):
-    """The fused FFN runs on CTA pairs (cta_group::2) by default and the projections on single CTAs; the other
-    combinations (DDP_B200_FFN_PAIR=0, DDP_B200_GEMM_PAIR bit mask) must give the same answer.  The ragged grid
+    """The fused FFN and the output projection run on CTA pairs (cta_group::2) by default, value / sampling on single
+    CTAs; the other combinations (DDP_B200_FFN_PAIR=0, DDP_B200_GEMM_PAIR bit mask) must give the same answer.  The ragged grid
     (9 x 15 tokens, 2 images: 270 rows = 3 row tiles) leaves the second CTA of the last pair without rows."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
