@@ -57,6 +57,7 @@ def class_cost(name, wl):
     table = {
         "value_proj": (2 * E * E, 4 * (E + E)),
         "sampling_proj": (2 * E * 96, 4 * (E + 96 + 96)),
+        "qproj_fused": (2 * E * E + 2 * E * 96, 4 * (E + E + 96 + 96)),  # value + sampling from one read of q
         "msda_gather": (2 * 8 * 4 * 4 * 32 + 0, 4 * (E + 96 + E)),
         "out_proj_ln": (2 * E * E, 4 * (E + E + E)),
         "ffn1_gelu": (2 * E * FFN, 4 * (E + FFN)),

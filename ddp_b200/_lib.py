@@ -24,7 +24,7 @@ EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "dd
            "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_head_forward", "ddp_resize_argmax", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
            "ddp_profile_collect", "ddp_kernel_class_name"]
-K_COUNT = 13
+K_COUNT = 14
 
 
 class DDPConfig(ctypes.Structure):

@@ -17,6 +17,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "ffn_fused.cuh"
+#include "qproj_fused.cuh"
 #include "kernels.cuh"
 
 using namespace ddp;
@@ -72,6 +73,7 @@ struct ddp_handle {
     // tcgen05 path (gemm_mode != FP32)
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
+    bool qproj_fused = false;   // value + sampling projections in one kernel (qproj_fused.cuh), DDP_B200_QPROJ_FUSED
     int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
     unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
@@ -446,6 +448,8 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
         if ((rc = make_tc_weight(h, T.o, cur, kE, kE, 256, {{wp->dev, &wp->host, kE, kE, 1, 0, 0}}, st, kE))) return rc;
         if ((rc = make_tc_weight(h, T.f1, cur, kFFN, kE, 256, {{w1->dev, &w1->host, kFFN, kE, 1, 0, 0}}, st))) return rc;
         if ((rc = make_tc_weight(h, T.f2, cur, kE, kFFN, 256, {{w2->dev, &w2->host, kE, kFFN, 1, 0, 0}}, st, kE))) return rc;
+        if (!tc::make_map_f16(&T.v.map_half_hi, T.v.hi, kE, kE, 64) || !tc::make_map_f16(&T.v.map_half_lo, T.v.lo, kE, kE, 64))
+            return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the value weight half-tile maps");
         if (!tc::make_map_f16(&T.f1.map_alt_hi, T.f1.hi, kFFN, kE, 128) || !tc::make_map_f16(&T.f1.map_alt_lo, T.f1.lo, kFFN, kE, 128) ||
             !tc::make_map_f16(&T.f2.map_alt_hi, T.f2.hi, kE, kFFN + kE, 128) || !tc::make_map_f16(&T.f2.map_alt_lo, T.f2.lo, kE, kFFN + kE, 128))
             return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for the fused-FFN weight maps");
@@ -596,6 +600,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         h->fuse_ffn = h->tc && (e == nullptr || atoi(e) != 0);
         const char* ge = getenv("DDP_B200_GEMM_PAIR");
         h->gemm_pair = !h->tc ? 0 : (ge != nullptr ? atoi(ge) : 4);     // default: output projection on pairs (12.6 -> 11.3 ms / sample)
+        const char* qe = getenv("DDP_B200_QPROJ_FUSED");
+        h->qproj_fused = h->tc && (qe == nullptr || atoi(qe) != 0);   // default on; 0 = separate value / sampling GEMMs
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         const char* d = getenv("DDP_B200_FFN_DBG");
@@ -875,6 +881,22 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
         const float* film = film_base + (size_t)j * 2 * kE;
         if (h->tc) {
             const TcLayer& T = h->tcL[j];
+            bool want_s = false;
+            for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
+            if (h->qproj_fused) {   // value and sampling projections from ONE read of q's planes
+                tc::QprojParams qp{};
+                qp.scale_v = T.v.inv_scale; qp.bias_v = L.bv; qp.V = ws.V;
+                qp.samp.scale = T.s.inv_scale; qp.samp.out = want_s ? ws.samp : nullptr; qp.samp.ldc = kSampW; qp.samp.ncols = kSampW;
+                qp.samp.pew = h->pew[j]; qp.samp.N_tok = N; qp.samp.rec = ws.rec; qp.samp.H = h->H; qp.samp.W = h->W;
+                prof_begin(h, DDP_K_QPROJ_FUSED, st);
+                cudaError_t e_ = s3 ? tc::launch_qproj_fused<3>(h->mA_q[0], h->mA_q[1], T.v.map_half_hi, T.v.map_half_lo,
+                                                                T.s.map_pair_hi, T.s.map_pair_lo, M, kE, qp, h->num_sms, st)
+                                    : tc::launch_qproj_fused<1>(h->mA_q[0], h->mA_q[0], T.v.map_half_hi, T.v.map_half_hi,
+                                                                T.s.map_pair_hi, T.s.map_pair_hi, M, kE, qp, h->num_sms, st);
+                prof_end(h, st);
+                if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused q-projection setup failed: %s", cudaGetErrorString(e_));
+                LAUNCH_CHECK(h);
+            } else {
             {   // value = value_proj(q)            (value uses q WITHOUT the positional encoding)
                 tc::EpiParams ep{};
                 ep.scale = T.v.inv_scale; ep.bias = L.bv; ep.out = ws.V; ep.ldc = kE; ep.ncols = kE;
@@ -882,11 +904,10 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
             }
             {   // offsets / attention weights = proj(q + pos) = q W^T + pew
                 tc::EpiParams ep{};
-                bool want_s = false;
-                for (const Tap& t : h->taps) want_s = want_s || (t.kind == DDP_TAP_SAMPLING && t.step == k && t.layer == j);
                 ep.scale = T.s.inv_scale; ep.out = want_s ? ws.samp : nullptr; ep.ldc = kSampW; ep.ncols = kSampW;
                 ep.pew = h->pew[j]; ep.N_tok = N; ep.rec = ws.rec; ep.H = h->H; ep.W = h->W;
                 TC_GEMMP(2, h, DDP_K_SAMPLING, st, 128, tc::EPI_SAMPLING, h->mA_q, T.s, M, 128, ep);
+            }
             }
             if ((rc = do_tap(h, DDP_TAP_VALUE, k, j, ws.V, (size_t)M * kE, st))) return rc;
             if ((rc = do_tap(h, DDP_TAP_SAMPLING, k, j, ws.samp, (size_t)M * kSampW, st))) return rc;   // written only when tapped
@@ -1134,7 +1155,7 @@ int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_
 const char* ddp_kernel_class_name(int cls) {
     static const char* names[DDP_K_COUNT] = {"cond", "head_in", "value_proj", "sampling_proj", "msda_gather", "out_proj_ln",
                                              "ffn1_gelu", "ffn2_ln_film", "head_out", "step_update", "finalize", "layout",
-                                             "ffn_fused"};
+                                             "ffn_fused", "qproj_fused"};
     return (cls >= 0 && cls < DDP_K_COUNT) ? names[cls] : nullptr;
 }
 

@@ -400,6 +400,63 @@ struct EpiParams {
     const float* ln_g; const float* ln_b;
 };
 
+// Sampling-projection epilogue of ONE warp.  Accumulator columns at t_row: 0..63 = (x, y) offsets of 32 sampling points
+// (head, point), 64..95 attention logits, 96..127 padding.  Four warps per TMEM lane quarter: warp `half` (0..3) owns
+// heads 2*half and 2*half + 1, i.e. offset columns [16 half, +16) and logits [64 + 8 half, +8); it writes the matching
+// 32-byte pieces of the four record sections (index words, fx, fy, attention weights).  `stg` = this warp's >= 1 KB tile.
+__device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t t_row, int half, int wrow0, size_t srow,
+                                                  int rows_valid, int lane, float* stg) {
+    const int n = (int)(srow % ep.N_tok);
+    __half* rech = reinterpret_cast<__half*>(ep.rec + (size_t)wrow0 * kRecW);       // 2 halves per record word
+    const float* pp = ep.pew + (size_t)n * kSampW;
+    float o[16], a[8];
+    tmem_ld16(t_row + 16 * half, o);
+    tmem_ld8(t_row + 64 + 8 * half, a);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 p4 = *reinterpret_cast<const float4*>(pp + 16 * half + i * 4);
+        o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
+        o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4);
+        a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
+        a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
+    }
+    if (ep.out) {                       // raw offsets for the test tap (fp32, 2 x 8 columns)
+        __half* oh = reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 16 * half);
+        stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[0]), oh, 2 * ep.ldc, rows_valid, lane);
+        stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[8]), oh + 16, 2 * ep.ldc, rows_valid, lane);
+    }
+    {
+        const int ti = n / ep.W, tj = n - ti * ep.W;
+        const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
+        const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
+        uint4 widx[2], wfx[2], wfy[2];
+        uint32_t* wi = reinterpret_cast<uint32_t*>(widx);
+        float* fxp = reinterpret_cast<float*>(wfx);
+        float* fyp = reinterpret_cast<float*>(wfy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
+        stage_store_32b(stg, widx, rech + 2 * (8 * half), 2 * kRecW, rows_valid, lane);
+        stage_store_32b(stg, wfx, rech + 2 * (32 + 8 * half), 2 * kRecW, rows_valid, lane);
+        stage_store_32b(stg, wfy, rech + 2 * (64 + 8 * half), 2 * kRecW, rows_valid, lane);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {       // softmax over each head's 4 points
+        const float mx = fmaxf(fmaxf(a[g * 4], a[g * 4 + 1]), fmaxf(a[g * 4 + 2], a[g * 4 + 3]));
+        const float e0 = expf(a[g * 4] - mx), e1 = expf(a[g * 4 + 1] - mx), e2 = expf(a[g * 4 + 2] - mx), e3 = expf(a[g * 4 + 3] - mx);
+        const float sden = (e0 + e1) + (e2 + e3);
+        a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
+    }
+    stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]), rech + 2 * (96 + 8 * half), 2 * kRecW, rows_valid, lane);
+    if (ep.out)
+        stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]),
+                        reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 64 + 8 * half), 2 * ep.ldc, rows_valid, lane);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -697,59 +754,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         stage_store_f16_32(stg, lo, ep.split.lo + (size_t)wrow0 * ep.split.ld + col0, ep.split.ld, rows_valid, lane);
                 }
             } else if (EPI == EPI_SAMPLING) {
-                // accumulator columns: 0..63 = (x, y) offsets of 32 sampling points (head, point), 64..95 attention logits,
-                // 96..127 padding.  Four warps per lane quarter: warp `half` (0..3) owns heads 2*half and 2*half + 1, i.e.
-                // offset columns [16 half, +16) and logits [64 + 8 half, +8); it writes the matching 32-byte pieces of the
-                // four record sections (index words, fx, fy, attention weights).
-                const int n = (int)(srow % ep.N_tok);
-                __half* rech = reinterpret_cast<__half*>(ep.rec + (size_t)wrow0 * kRecW);       // 2 halves per record word
-                const float* pp = ep.pew + (size_t)n * kSampW;
-                float o[16], a[8];
-                tmem_ld16(t_row + 16 * half, o);
-                tmem_ld8(t_row + 64 + 8 * half, a);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 p4 = *reinterpret_cast<const float4*>(pp + 16 * half + i * 4);
-                    o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
-                    o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4);
-                    a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
-                    a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
-                }
-                if (ep.out) {                       // raw offsets for the test tap (fp32, 2 x 8 columns)
-                    __half* oh = reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 16 * half);
-                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[0]), oh, 2 * ep.ldc, rows_valid, lane);
-                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[8]), oh + 16, 2 * ep.ldc, rows_valid, lane);
-                }
-                {
-                    const int ti = n / ep.W, tj = n - ti * ep.W;
-                    const float refx = __fdiv_rn((float)tj + 0.5f, (float)ep.W), refy = __fdiv_rn((float)ti + 0.5f, (float)ep.H);
-                    const float rW = __frcp_rn((float)ep.W), rH = __frcp_rn((float)ep.H);
-                    uint4 widx[2], wfx[2], wfy[2];
-                    uint32_t* wi = reinterpret_cast<uint32_t*>(widx);
-                    float* fxp = reinterpret_cast<float*>(wfx);
-                    float* fyp = reinterpret_cast<float*>(wfy);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
-                    stage_store_32b(stg, widx, rech + 2 * (8 * half), 2 * kRecW, rows_valid, lane);
-                    stage_store_32b(stg, wfx, rech + 2 * (32 + 8 * half), 2 * kRecW, rows_valid, lane);
-                    stage_store_32b(stg, wfy, rech + 2 * (64 + 8 * half), 2 * kRecW, rows_valid, lane);
-                }
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {       // softmax over each head's 4 points
-                    const float mx = fmaxf(fmaxf(a[g * 4], a[g * 4 + 1]), fmaxf(a[g * 4 + 2], a[g * 4 + 3]));
-                    const float e0 = expf(a[g * 4] - mx), e1 = expf(a[g * 4 + 1] - mx), e2 = expf(a[g * 4 + 2] - mx), e3 = expf(a[g * 4 + 3] - mx);
-                    const float sden = (e0 + e1) + (e2 + e3);
-                    a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
-                }
-                stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]), rech + 2 * (96 + 8 * half), 2 * kRecW, rows_valid, lane);
-                if (ep.out)
-                    stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]),
-                                    reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 64 + 8 * half), 2 * ep.ldc, rows_valid, lane);
+                sampling_epilogue(ep, t_row, half, wrow0, srow, rows_valid, lane, stg);
             } else {
 #pragma unroll 1
                 for (int c = cbeg; c < cbeg + C::kColsPerWarp; c += 64) {

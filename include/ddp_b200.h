@@ -185,7 +185,7 @@ int64_t ddp_last_launch_count(const ddp_handle* h);
  * summed milliseconds and the number of launches since the last collect. */
 enum {
     DDP_K_COND = 0, DDP_K_HEAD_IN, DDP_K_VALUE, DDP_K_SAMPLING, DDP_K_GATHER, DDP_K_OUT_PROJ,
-    DDP_K_FFN1, DDP_K_FFN2, DDP_K_HEAD_OUT, DDP_K_STEP, DDP_K_FINALIZE, DDP_K_LAYOUT, DDP_K_FFN_FUSED, DDP_K_COUNT
+    DDP_K_FFN1, DDP_K_FFN2, DDP_K_HEAD_OUT, DDP_K_STEP, DDP_K_FINALIZE, DDP_K_LAYOUT, DDP_K_FFN_FUSED, DDP_K_QPROJ_FUSED, DDP_K_COUNT
 };
 int ddp_profile_enable(ddp_handle* h, int on);
 int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_class, int n_classes);

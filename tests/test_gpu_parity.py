@@ -440,8 +440,9 @@ def test_unfused_ffn_pair_still_correct(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"DDP_B200_FFN_PAIR": "0"}, {"DDP_B200_GEMM_PAIR": "7"},
-                                 {"DDP_B200_FFN_PAIR": "0", "DDP_B200_GEMM_PAIR": "0"}],
-                         ids=["ffn_single_cta", "all_gemm_pairs", "no_pairs"])
+                                 {"DDP_B200_FFN_PAIR": "0", "DDP_B200_GEMM_PAIR": "0"}, {"DDP_B200_QPROJ_FUSED": "1"},
+                                 {"DDP_B200_QPROJ_FUSED": "0"}],
+                         ids=["ffn_single_cta", "all_gemm_pairs", "no_pairs", "qproj_fused", "qproj_separate"])
 def test_cta_pair_options_agree_with_oracle(monkeypatch, env):
     """The fused FFN and the output projection run on CTA pairs (cta_group::2) by default, value / sampling on single
     CTAs; the other combinations (DDP_B200_FFN_PAIR=0, DDP_B200_GEMM_PAIR bit mask) must give the same answer.  The ragged grid
