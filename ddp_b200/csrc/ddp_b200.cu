@@ -604,6 +604,7 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         h->qproj_fused = h->tc && (qe == nullptr || atoi(qe) != 0);   // default on; 0 = separate value / sampling GEMMs
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
+        if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
         const char* d = getenv("DDP_B200_FFN_DBG");
         if (d && atoi(d) != 0 && cudaMalloc(&h->ffn_dbg, 64) == cudaSuccess) cudaMemset(h->ffn_dbg, 0, 64);
     }

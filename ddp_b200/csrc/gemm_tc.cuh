@@ -139,16 +139,19 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// arrive (release, cluster scope) on the leader's copy of `bar`
+// arrive on the leader's copy of `bar`.  Default semantics (release at CTA scope) on purpose: what is handed over is
+// tensor memory, ordered by tcgen05.fence::before_thread_sync / after_thread_sync around the barrier (the same
+// hand-shake CUTLASS's 2-SM kernels use); `.release.cluster` compiles to MEMBAR + ERRBAR + CCTL.IVALL (an L1 flush)
+// and cost ~15 % of the fused q-projection's warp samples (ncu source view, profiles/r01_notes.md).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_smem_u32(bar)) : "memory");
 }
-// cluster-scope acquire wait on this CTA's own barrier (pairs with arrivals from the peer CTA)
+// wait on this CTA's own barrier for arrivals that may come from the peer CTA (see mbar_arrive_leader for the semantics)
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
