@@ -10,10 +10,11 @@
 //   epilogue: LayerNorm + folded FiLM, fp16 planes (and optionally fp32) of the new q
 //
 // TMEM (512 columns): D2 [0,256) | D1 [256,384) | hid planes [384,512) (hi 64 + lo 64 columns).
-// The tensor core fetches shared-memory operands at ~64 B/clk, so an N=64 MMA1 (A 4 KB + B 2 KB per K=16 step) runs at a
-// third of its math rate; N=128 chunks halve that overhead, at the price of single-buffered D1 / hid (TMEM is full).
-// Warps: 0 TMA producer (A1 + a 4-stage ring of 16 KB weight units), 1 MMA issuer, 2..17 epilogue (thread = row,
-// four warps per TMEM lane quarter).  MMA1 of chunk c+1 overlaps the GELU epilogue and MMA2 of chunk c.
+// An SS-mode N=64 MMA is operand-fetch bound (48 instead of 32 cycles, tools/ubench_mma.cu) while N=128 runs at the math
+// rate: hence 128-wide hidden chunks, at the price of single-buffered D1 / hid (TMEM is full).
+// Warps: 0 TMA producer (A1 + a ring of [hi | lo] weight units), 1 MMA issuer, 2..17 epilogue (thread = row, four
+// warps per TMEM lane quarter).  MMA1 of chunk c+1 overlaps the GELU epilogue and MMA2 of chunk c.
+// By default the kernel runs on CTA pairs (template PAIR, see below): 256 tokens per pair, cta_group::2 MMAs.
 #pragma once
 #include "gemm_tc.cuh"
 

@@ -7,7 +7,8 @@
 // fp16 x fp16 products are exact in fp32, so the result is fp32-faithful (DDP_GEMM_TC_3XF16).
 // NSPLIT == 1 issues only the hi*hi MMA (DDP_GEMM_TC_F16, fast, not parity-grade).
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 320 threads; 576 with the 16-warp sampling / GELU epilogues; template PAIR
+// runs the same kernel on CTA pairs with cta_group::2 MMAs, see Cfg):
 //   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A_hi, A_lo, W_hi, W_lo
 //            into a ring of shared-memory stages, completion on mbarriers.
 //   warp 1   MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) on
