@@ -157,6 +157,9 @@ class DecodeEngine:
         assert x.is_cuda and noise.is_cuda and x.dtype == torch.float32 and noise.dtype == torch.float32
         x = x.contiguous()
         noise = noise.contiguous()
+        if B == 0:                      # empty batch: nothing to launch (the C ABI itself rejects B < 1)
+            out = torch.empty((0, self.num_classes, h, w), dtype=torch.float32, device=x.device)
+            return (out, torch.empty((0, h, w), dtype=torch.int32, device=x.device)) if (return_cls and self.task == "seg") else out
         self.plan(B, R, h, w)
         out = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=x.device)
         cls = torch.empty((B, h, w), dtype=torch.int32, device=x.device) if (return_cls and self.task == "seg") else None

@@ -263,6 +263,11 @@ def test_error_behaviour_mirrors_reference():
     eng.load_state_dict({**W, "backbone.stem.weight": torch.zeros(3)})      # extra keys are ignored
     with pytest.raises(DDPError):
         DecodeEngine(num_classes=300)
+    # empty batch: torch semantics at the Python layer (an empty result, nothing launched); the C ABI rejects B < 1
+    out, cls = eng.sample(torch.zeros(0, 256, 4, 4).cuda(), torch.zeros(0, 1, 256, 4, 4).cuda(), return_cls=True)
+    assert tuple(out.shape) == (0, 19, 4, 4) and tuple(cls.shape) == (0, 4, 4)
+    with pytest.raises(DDPError, match="must be >= 1"):
+        eng.plan(0, 1, 4, 4)
 
 
 def test_library_schedule_close_to_reference_schedule():
