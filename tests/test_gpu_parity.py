@@ -263,11 +263,6 @@ def test_error_behaviour_mirrors_reference():
     eng.load_state_dict({**W, "backbone.stem.weight": torch.zeros(3)})      # extra keys are ignored
     with pytest.raises(DDPError):
         DecodeEngine(num_classes=300)
-    # empty batch: torch semantics at the Python layer (an empty result, nothing launched); the C ABI rejects B < 1
-    out, cls = eng.sample(torch.zeros(0, 256, 4, 4).cuda(), torch.zeros(0, 1, 256, 4, 4).cuda(), return_cls=True)
-    assert tuple(out.shape) == (0, 19, 4, 4) and tuple(cls.shape) == (0, 4, 4)
-    with pytest.raises(DDPError, match="must be >= 1"):
-        eng.plan(0, 1, 4, 4)
 
 
 def test_library_schedule_close_to_reference_schedule():
@@ -488,3 +483,14 @@ def test_full_size_depth_properties():
     assert a.min().item() >= cfg.min_depth - 1e-7 and a.max().item() <= cfg.max_depth + 1e-6
     solo = eng.sample(x[1:2].cuda(), noise[1:2].cuda())
     assert torch.equal(solo, a[1:2])
+
+
+def test_empty_batch():
+    """Empty input: torch semantics at the Python layer (an empty result, nothing launched); the C ABI rejects B < 1."""
+    from ddp_b200._lib import DDPError
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    eng = make_engine(cfg, O.make_weights(cfg, seed=2), "tc_3xf16")
+    out, cls = eng.sample(torch.zeros(0, 256, 4, 4).cuda(), torch.zeros(0, 1, 256, 4, 4).cuda(), return_cls=True)
+    assert tuple(out.shape) == (0, 19, 4, 4) and tuple(cls.shape) == (0, 4, 4)
+    with pytest.raises(DDPError, match="must be >= 1"):
+        eng.plan(0, 1, 4, 4)
