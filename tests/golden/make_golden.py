@@ -2,6 +2,7 @@
 
     python tests/golden/make_golden.py seg
     python tests/golden/make_golden.py depth
+    python tests/golden/make_golden.py neck
 
 Runs only in the build container (needs /root/reference).  It builds the
 reference's own classes from the reference's own config files
@@ -30,6 +31,7 @@ warnings.filterwarnings("ignore")
 
 import refshim  # noqa: E402
 from oracle import ddp_oracle as O  # noqa: E402
+from oracle import neck_oracle as NO  # noqa: E402
 
 SEG_CASES = [
     # name, config file, class override, num_classes, T, R, accumulation, h, w, wseed, xseed
@@ -52,6 +54,17 @@ DEPTH_CASES = [
          T=None, R=1, h=12, w=16, wseed=21, xseed=201),
     dict(name="depth_nyu_T20_R2", cfg="ddp_nyu/ddp_swint_1k_w7_nyu_bs2x8_scale01.py",
          T=20, R=2, h=9, w=11, wseed=22, xseed=202),
+]
+
+# the neck in front of the loop: FPN + MultiStageMerging built from the reference's config files
+NECK_CASES = [
+    dict(name="neck_swin_t_city", tree="segmentation", cfg="cityscapes/ddp_swin_t_4x4_512x1024_160k_cityscapes.py",
+         B=1, h=12, w=20, wseed=31, xseed=301),
+    dict(name="neck_swin_l_ade", tree="segmentation", cfg="ade/ddp_swin_l_2x8_512x512_160k_ade20k.py",
+         B=2, h=8, w=8, wseed=32, xseed=302),
+    # odd pyramid sizes (15x20 -> 8x10 -> 4x5 -> 2x3): nearest / bilinear ratios that are not exactly 2
+    dict(name="neck_convnext_t_odd", tree="segmentation",
+         cfg="cityscapes/ddp_convnext_t_4x4_512x1024_5k_cityscapes_aligned.py", B=1, h=15, w=20, wseed=33, xseed=303),
 ]
 
 
@@ -214,5 +227,43 @@ def run_depth():
         print(case["name"], tuple(out.shape), float(out.mean()), float(out.min()), float(out.max()))
 
 
+def run_neck():
+    refshim.install("segmentation")
+    for n in ("mmcls", "mmcls.models"):
+        sys.modules[n] = types.ModuleType(n)
+    import mmcv  # noqa: F401
+    from mmcv import Config
+    import mmseg.models  # noqa: F401  (registers FPN / MultiStageMerging)
+    from mmseg.models import builder
+
+    for case in NECK_CASES:
+        cfg = Config.fromfile(f"{refshim.REF}/{case['tree']}/configs/{case['cfg']}")
+        ncfg = cfg.model.neck
+        neck = builder.build_neck(ncfg)                      # Sequential(FPN, MultiStageMerging), neck.0.* / neck.1.*
+        neck.eval()
+        in_channels = list(ncfg[0].in_channels)
+        W = NO.make_weights(in_channels, seed=case["wseed"])
+        sd = neck.state_dict()
+        assert sorted("neck." + k for k in sd) == sorted(W), (sorted(sd), sorted(W))
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(W["neck." + k].shape), k
+        neck.load_state_dict({k[len("neck."):]: v for k, v in W.items()})
+        xs = NO.make_inputs(in_channels, case["B"], case["h"], case["w"], seed=case["xseed"])
+        with torch.no_grad():
+            fpn_outs = neck[0](tuple(xs))
+            out = neck[1](fpn_outs)
+            assert isinstance(out, list) and len(out) == 1
+            whole = neck(tuple(xs))[0]
+        assert torch.equal(whole, out[0])
+        np.savez_compressed(
+            os.path.join(HERE, case["name"] + ".npz"),
+            task="neck", config=case["cfg"], in_channels=np.array(in_channels), B=case["B"], h=case["h"], w=case["w"],
+            wseed=case["wseed"], xseed=case["xseed"],
+            x_checksum=checksum(torch.cat([x.flatten() for x in xs])),
+            w_checksum=checksum(torch.cat([v.flatten() for _, v in sorted(W.items())])),
+            out=out[0].numpy(), **{f"fpn{i}": o.numpy() for i, o in enumerate(fpn_outs)})
+        print(case["name"], in_channels, tuple(out[0].shape), float(out[0].abs().mean()))
+
+
 if __name__ == "__main__":
-    {"seg": run_seg, "depth": run_depth}[sys.argv[1]]()
+    {"seg": run_seg, "depth": run_depth, "neck": run_neck}[sys.argv[1]]()

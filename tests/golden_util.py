@@ -6,14 +6,20 @@ import numpy as np
 import torch
 
 from oracle import ddp_oracle as O
+from oracle import neck_oracle as NO
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+LOOP_TASKS = ("seg", "depth")          # fixtures of the decode loop; "neck" fixtures are loaded by load_neck_case
+
+
 def golden_files(task=None):
+    """Fixtures whose file name starts with `task`; default: every decode-loop fixture (seg_*, depth_*)."""
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
-        if task is None or os.path.basename(f).startswith(task):
+        name = os.path.basename(f)
+        if name.startswith(task if task is not None else LOOP_TASKS):
             out.append(f)
     return out
 
@@ -53,3 +59,16 @@ def load_case(path):
     wsum = checksum(torch.cat([v.flatten() for _, v in sorted(W.items())]))
     assert np.allclose(wsum, g["w_checksum"], rtol=0, atol=1e-5), "weight regeneration drifted"
     return cfg, W, x, noise, g
+
+
+def load_neck_case(path):
+    """-> (W, inputs [4 x (B,C_l,h_l,w_l)], golden dict) of a neck_*.npz fixture."""
+    g = dict(np.load(path, allow_pickle=False))
+    assert str(g["task"]) == "neck"
+    in_channels = [int(c) for c in g["in_channels"]]
+    W = NO.make_weights(in_channels, seed=int(g["wseed"]))
+    xs = NO.make_inputs(in_channels, int(g["B"]), int(g["h"]), int(g["w"]), seed=int(g["xseed"]))
+    assert np.allclose(checksum(torch.cat([x.flatten() for x in xs])), g["x_checksum"], rtol=0, atol=1e-6)
+    wsum = checksum(torch.cat([v.flatten() for _, v in sorted(W.items())]))
+    assert np.allclose(wsum, g["w_checksum"], rtol=0, atol=1e-5), "weight regeneration drifted"
+    return W, xs, g

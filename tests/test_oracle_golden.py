@@ -7,7 +7,8 @@ import pytest
 import torch
 
 from oracle import ddp_oracle as O
-from golden_util import golden_files, load_case
+from oracle import neck_oracle as NO
+from golden_util import golden_files, load_case, load_neck_case
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
@@ -107,3 +108,32 @@ def test_fp64_mode_close_to_fp32():
     o32 = O.sample(W, cfg, x, noise)
     o64 = O.sample(O.cast_weights(W, torch.float64), cfg, x.double(), noise.double())
     assert (o32.double() - o64).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("path", golden_files("neck"), ids=lambda p: os.path.basename(p)[:-4])
+def test_neck_oracle_matches_reference_output(path):
+    """FPN + MultiStageMerging restatement vs the unmodified reference modules (make_golden.py neck)."""
+    W, xs, g = load_neck_case(path)
+    trace = {}
+    out = NO.neck(W, xs, trace)
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    # same ATen ops in the same order on the same CPU: bit-for-bit
+    assert torch.equal(out, ref), f"max |d| = {(out - ref).abs().max().item():.3e}"
+    for i, o in enumerate(trace["fpn"]):
+        assert torch.equal(o, torch.from_numpy(g[f"fpn{i}"])), f"fpn level {i}"
+
+
+def test_neck_merge_commutes_with_the_1x1_conv():
+    """The CUDA neck applies the 1x1 `down` conv per level BEFORE the bilinear resize (both are linear, the conv acts
+    on channels, the resize on space): same result up to fp32 summation order."""
+    import torch.nn.functional as F
+    W = NO.make_weights([96, 192, 384, 768], seed=5)
+    xs = NO.make_inputs([96, 192, 384, 768], 2, 9, 14, seed=6)
+    outs = NO.fpn(W, xs)
+    wd = W["neck.1.down.conv.weight"]
+    pre = sum(F.interpolate(F.conv2d(o, wd[:, 256 * l:256 * (l + 1)]), size=outs[0].shape[2:], mode="bilinear",
+                            align_corners=False) for l, o in enumerate(outs))
+    got = F.group_norm(pre, NO.GROUPS, W["neck.1.down.gn.weight"], W["neck.1.down.gn.bias"], NO.EPS)
+    want = NO.multi_stage_merging(W, outs)
+    assert (got - want).abs().max().item() < 2e-5
