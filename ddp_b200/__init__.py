@@ -7,3 +7,4 @@ plug-in surface (DDP / SelfAlignedDDP / DeformableHeadWithTime) of the reference
 __version__ = "0.1.0"
 
 from .engine import DecodeEngine  # noqa: F401
+from .neck import NeckEngine  # noqa: F401

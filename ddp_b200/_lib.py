@@ -23,7 +23,11 @@ EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "dd
            "ddp_weight_name", "ddp_set_weight", "ddp_commit_weights", "ddp_set_schedule",
            "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_head_forward", "ddp_resize_argmax", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
-           "ddp_profile_collect", "ddp_kernel_class_name"]
+           "ddp_profile_collect", "ddp_kernel_class_name",
+           "ddp_neck_create", "ddp_neck_destroy", "ddp_neck_last_error", "ddp_neck_weight_count", "ddp_neck_weight_name",
+           "ddp_neck_set_weight", "ddp_neck_commit_weights", "ddp_neck_plan", "ddp_neck_forward",
+           "ddp_neck_last_launch_count"]
+NECK_STAGE_FPN, NECK_STAGE_MERGE = 1, 2
 K_COUNT = 14
 
 
@@ -35,6 +39,12 @@ class DDPConfig(ctypes.Structure):
                 ("num_layers", ctypes.c_int32), ("gemm_mode", ctypes.c_int32),
                 ("sample_range_lo", ctypes.c_float), ("bit_scale", ctypes.c_float),
                 ("min_depth", ctypes.c_float), ("max_depth", ctypes.c_float)]
+
+
+class DDPNeckConfig(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("stages", ctypes.c_int32), ("num_levels", ctypes.c_int32),
+                ("in_channels", ctypes.c_int32 * 4), ("out_channels", ctypes.c_int32), ("num_groups", ctypes.c_int32),
+                ("eps", ctypes.c_float)]
 
 
 class DDPError(RuntimeError):
@@ -87,6 +97,21 @@ def load():
     lib.ddp_profile_collect.argtypes = [vp, fp, ctypes.POINTER(i64), i32]
     lib.ddp_kernel_class_name.argtypes = [i32]
     lib.ddp_kernel_class_name.restype = cp
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    lib.ddp_neck_create.argtypes = [ctypes.POINTER(DDPNeckConfig), ctypes.POINTER(vp)]
+    lib.ddp_neck_destroy.argtypes = [vp]
+    lib.ddp_neck_destroy.restype = None
+    lib.ddp_neck_last_error.argtypes = [vp]
+    lib.ddp_neck_last_error.restype = cp
+    lib.ddp_neck_weight_count.argtypes = [vp]
+    lib.ddp_neck_weight_name.argtypes = [vp, i32, ctypes.POINTER(i64)]
+    lib.ddp_neck_weight_name.restype = cp
+    lib.ddp_neck_set_weight.argtypes = [vp, cp, vp, i64]
+    lib.ddp_neck_commit_weights.argtypes = [vp]
+    lib.ddp_neck_plan.argtypes = [vp, i32, i32p, i32p, ctypes.POINTER(ctypes.c_size_t)]
+    lib.ddp_neck_forward.argtypes = [vp, ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp, ctypes.c_size_t, vp]
+    lib.ddp_neck_last_launch_count.argtypes = [vp]
+    lib.ddp_neck_last_launch_count.restype = i64
     if lib.ddp_abi_version() != ABI_VERSION:
         raise ImportError(f"libddp_b200.so ABI {lib.ddp_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

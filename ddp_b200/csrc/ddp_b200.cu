@@ -1255,3 +1255,6 @@ int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host,
 }
 
 }  // extern "C"
+
+// The neck in front of the loop (FPN + MultiStageMerging): its own handle type and entry points.
+#include "neck.cuh"

@@ -10,6 +10,7 @@
 // multiple of BN) so B-tile loads are coalesced float4 and need no bounds checks.
 #pragma once
 #include "common.cuh"
+#include "neck_plan.h"
 
 namespace ddp {
 
@@ -185,10 +186,13 @@ struct EpiResidualLN {
 };
 
 // ---- kernel ----------------------------------------------------------------------------------
-// A_KN == false: A is row-major [M][lda].
-// A_KN == true : A is a stack of images in NCHW, element (m, k) = A[(m / n_img) * K * n_img + k * n_img + m % n_img]
-//                (reads the neck feature x without a transposed copy).
-template <int BM, int BN, bool A_KN, class Epi>
+// A_MODE == 0 (false): A is row-major [M][lda].
+// A_MODE == 1 (true) : A is a stack of images in NCHW, element (m, k) = A[(m / n_img) * K * n_img + k * n_img + m % n_img]
+//                      (reads the neck feature x / the backbone maps without a transposed copy).
+// A_MODE == 2        : 3x3 convolution, padding 1, over token-major images [imgs][n_img][K / 9] of width `lda`:
+//                      element (m, k) = channel k % (K/9) of the token shifted by tap k / (K/9), zero outside
+//                      (neck::conv3_src_offset; the FPN output convs, segmentation/mmseg/models/necks/fpn.py:130-139).
+template <int BM, int BN, int A_MODE, class Epi>
 __global__ void __launch_bounds__(256, 2)
 gemm_simt_kernel(const float* __restrict__ A, int lda, int n_img, const float* __restrict__ Wt, int ldw,
                  int M, int K, Epi epi) {
@@ -218,10 +222,18 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, int n_img, const float* _
     const int k_k = tid >> 4, k_rq = (tid & 15) * 4;           // KN loader
 
     auto load_tiles = [&](int k0) {
-        if (!A_KN) {
+        if (A_MODE == 0) {
             int row = m0 + a_row;
             if (row >= M) row = M - 1;
             float4 v = *reinterpret_cast<const float4*>(A + (size_t)row * lda + k0 + a_kq);
+            a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
+        } else if (A_MODE == 2) {
+            // the 4 consecutive k of this thread share one tap (K / 9 is a multiple of 16) -> one float4 or zeros
+            int row = m0 + a_row;
+            if (row >= M) row = M - 1;
+            const long long off = neck::conv3_src_offset(row, k0 + a_kq, n_img, lda, K / 9);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (off >= 0) v = *reinterpret_cast<const float4*>(A + off);
             a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
         } else {
 #pragma unroll
@@ -240,7 +252,7 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, int n_img, const float* _
         }
     };
     auto store_tiles = [&](int buf) {
-        if (!A_KN) {
+        if (A_MODE != 1) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) As[buf][a_kq + i][a_row] = a_reg[i];
         } else {
@@ -287,11 +299,11 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, int n_img, const float* _
     epi(acc, m0 + ty * TM, tx, n0);
 }
 
-template <int BN, bool A_KN, class Epi>
+template <int BN, int A_MODE, class Epi>
 inline void launch_gemm_simt(const float* A, int lda, int n_img, const float* Wt, int ldw, int M, int K,
                                     int ncols_padded, const Epi& epi, cudaStream_t st) {
     dim3 grid((M + 63) / 64, ncols_padded / BN);
-    gemm_simt_kernel<64, BN, A_KN, Epi><<<grid, 256, 0, st>>>(A, lda, n_img, Wt, ldw, M, K, epi);
+    gemm_simt_kernel<64, BN, A_MODE, Epi><<<grid, 256, 0, st>>>(A, lda, n_img, Wt, ldw, M, K, epi);
 }
 
 }  // namespace ddp

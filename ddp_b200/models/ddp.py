@@ -56,7 +56,8 @@ def _build_encoder_part(cfg):
     if cfg is None:
         return None
     if isinstance(cfg, (list, tuple)):
-        return nn.Sequential(*[_build_encoder_part(c) for c in cfg])
+        from ..neck import fuse_neck       # neck=[FPN, MultiStageMerging] runs as one library call
+        return fuse_neck([_build_encoder_part(c) for c in cfg])
     typ = cfg.get("type")
     if isinstance(typ, str) and typ not in MODELS:
         warnings.warn(f"'{typ}' is not registered; using a placeholder (the encoder is outside the ddp_b200 hot path)")

@@ -191,6 +191,60 @@ int ddp_profile_enable(ddp_handle* h, int on);
 int ddp_profile_collect(ddp_handle* h, float* ms_by_class, int64_t* launches_by_class, int n_classes);
 const char* ddp_kernel_class_name(int cls);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The neck in front of the loop: FPN + MultiStageMerging, the module pair every DDP config chains
+ * between backbone and decode head.  It produces `x`, the frozen conditioning feature ddp_sample takes.
+ *
+ * Reference interfaces replaced:
+ *   ddp_neck_create / set_weight   FPN.__init__                   segmentation/mmseg/models/necks/fpn.py:66-160
+ *                                  MultiStageMerging.__init__     segmentation/mmseg/models/necks/multi_stage_merging.py:14-37
+ *   ddp_neck_forward               FPN.forward                    segmentation/mmseg/models/necks/fpn.py:162-213
+ *                                  MultiStageMerging.forward      segmentation/mmseg/models/necks/multi_stage_merging.py:40-52
+ *                                  (depth/depth/models/necks/{fpn,multi_stage_merging}.py are copies)
+ * Supported arguments = what the DDP configs pass: out_channels 256, GroupNorm after every conv (no conv bias),
+ * act_cfg None, num_outs == number of inputs, start_level 0, nearest top-down upsampling, bilinear
+ * align_corners=False merging; in_channels multiples of 16.  Same conventions as above (caller-owned device memory,
+ * asynchronous on `stream`, no allocation after ddp_neck_commit_weights, status codes, no CPU path).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ddp_neck ddp_neck;
+
+enum { DDP_NECK_STAGE_FPN = 1, DDP_NECK_STAGE_MERGE = 2 };   /* stages bit mask: 1 = FPN only, 2 = MultiStageMerging only, 3 = fused */
+
+typedef struct ddp_neck_config {
+    int32_t abi_version;        /* DDP_ABI_VERSION */
+    int32_t stages;             /* DDP_NECK_STAGE_* bit mask */
+    int32_t num_levels;         /* len(in_channels) == num_outs, <= 4 */
+    int32_t in_channels[4];     /* FPN(in_channels=); ignored (256 each) when stages == MERGE */
+    int32_t out_channels;       /* 256 */
+    int32_t num_groups;         /* norm_cfg=dict(type='GN', num_groups=32) */
+    float   eps;                /* 1e-5 (nn.GroupNorm default) */
+} ddp_neck_config;
+
+int ddp_neck_create(const ddp_neck_config* cfg, ddp_neck** out);
+void ddp_neck_destroy(ddp_neck* h);
+const char* ddp_neck_last_error(const ddp_neck* h);   /* h may be NULL: last create error */
+
+/* Weights by the reference's state-dict key, contiguous fp32 HOST arrays in the reference's shapes.  The key may carry
+ * the module path in front ("neck.0.lateral_convs.2.conv.weight", "0.lateral_convs.2.conv.weight" and
+ * "lateral_convs.2.conv.weight" are the same tensor): lateral_convs.{l}.conv.weight (256,C_l,1,1),
+ * fpn_convs.{l}.conv.weight (256,256,3,3), {lateral_convs,fpn_convs}.{l}.gn.{weight,bias} (256), down.conv.weight
+ * (256,256*L,1,1), down.gn.{weight,bias}. */
+int ddp_neck_weight_count(const ddp_neck* h);
+const char* ddp_neck_weight_name(const ddp_neck* h, int index, int64_t* numel);
+int ddp_neck_set_weight(ddp_neck* h, const char* name, const float* host_data, int64_t numel);
+int ddp_neck_commit_weights(ddp_neck* h);
+
+/* Fix the geometry: B images, level l is heights[l] x widths[l] (level 0 = the 1/4-resolution map the decode loop runs on). */
+int ddp_neck_plan(ddp_neck* h, int B, const int32_t* heights, const int32_t* widths, size_t* workspace_bytes);
+
+/*   inputs[l]    (B,C_l,h_l,w_l) fp32 NCHW device      backbone pyramid (stages & FPN) or FPN outputs (stages == MERGE)
+ *   x_out        (B,256,h_0,w_0) fp32 NCHW device      MultiStageMerging output; may be NULL when stages == FPN
+ *   fpn_outs[l]  (B,256,h_l,w_l) fp32 NCHW device      FPN outputs; the array or single entries may be NULL unless stages == FPN
+ * workspace: >= ddp_neck_plan's size, 256-byte aligned. */
+int ddp_neck_forward(ddp_neck* h, const float* const* inputs, float* x_out, float* const* fpn_outs, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int64_t ddp_neck_last_launch_count(const ddp_neck* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,9 @@ from ddp_b200.config import Config
 from ddp_b200.registry import MODELS, build_segmentor, build_depther
 import ddp_b200.models as M
 from ddp_b200 import dist as D
+from ddp_b200.neck import FPN, FusedNeck, MultiStageMerging
 from oracle import ddp_oracle as O
+from oracle import neck_oracle as NO
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
@@ -87,6 +89,31 @@ def test_constructor_errors_mirror_reference():
         build_segmentor(dict(type="NoSuchSegmentor"))
 
 
+def test_neck_plugin_surface():
+    """FPN / MultiStageMerging: reference constructor arguments and state-dict keys; arguments outside what the DDP
+    configs use are refused loudly; without a GPU the forward fails loudly (no CPU fallback)."""
+    gn = dict(type="GN", num_groups=32)
+    fpn = MODELS.build(dict(type="FPN", in_channels=[96, 192, 384, 768], out_channels=256, act_cfg=None, norm_cfg=gn,
+                            num_outs=4))
+    msm = MODELS.build(dict(type="MultiStageMerging", in_channels=[256] * 4, out_channels=256, kernel_size=1,
+                            norm_cfg=gn, act_cfg=None))
+    assert isinstance(fpn, FPN) and isinstance(msm, MultiStageMerging)
+    want = NO.make_weights([96, 192, 384, 768], seed=0)
+    got = {"neck.0." + k: v for k, v in fpn.state_dict().items()}
+    got.update({"neck.1." + k: v for k, v in msm.state_dict().items()})
+    assert set(got) == set(want) and all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
+    for bad in (dict(num_outs=5), dict(add_extra_convs=True), dict(norm_cfg=dict(type="BN")), dict(norm_cfg=None),
+                dict(act_cfg=dict(type="ReLU")), dict(upsample_cfg=dict(mode="bilinear")), dict(start_level=1)):
+        with pytest.raises(NotImplementedError):
+            MODELS.build({**dict(type="FPN", in_channels=[96, 192, 384, 768], out_channels=256, norm_cfg=gn, num_outs=4),
+                          **bad})
+    with pytest.raises(NotImplementedError):
+        MODELS.build(dict(type="MultiStageMerging", in_channels=[256] * 4, out_channels=256, kernel_size=3, norm_cfg=gn))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fpn([torch.zeros(1, c, 4, 4) for c in (96, 192, 384, 768)])
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 def test_reference_config_files_build_unchanged():
     files = sorted(glob.glob(f"{REF}/segmentation/configs/*/ddp_*.py"))
@@ -98,12 +125,18 @@ def test_reference_config_files_build_unchanged():
             model = build_segmentor(cfg.model)
             assert type(model).__name__ == cfg.model.type
             assert model.timesteps == cfg.model.timesteps and model.bit_scale == 0.01
+            # the neck pair of every config builds into the fused CUDA neck with the reference's state-dict keys
+            assert isinstance(model.neck, FusedNeck)
+            want = NO.make_weights(list(cfg.model.neck[0].in_channels), seed=0)
+            got = {k: v for k, v in model.state_dict().items() if k.startswith("neck.")}
+            assert set(got) == set(want) and all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
         dfiles = sorted(glob.glob(f"{REF}/depth/configs/ddp_*/*.py"))
         assert len(dfiles) == 8
         for f in dfiles:
             cfg = Config.fromfile(f)
             model = build_depther(cfg.model)
             assert model.max_depth == cfg.model.max_depth
+            assert isinstance(model.neck, FusedNeck)
 
 
 def test_shard_bounds_cover_batch():

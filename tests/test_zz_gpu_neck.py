@@ -1,0 +1,146 @@
+"""GPU parity tests of the neck (FPN + MultiStageMerging) through the C ABI: against the golden outputs
+of the unmodified reference modules and against the oracle.
+
+STATUS: this row was built after the round-1 GPU budget was spent.  Its launch sequence and kernel bodies are checked
+against the oracle by the host emulation (tests/test_neck_emu_cpu.py); the CUDA build itself has not run on hardware
+yet, hence `first_hw_run` (collected last, non-strict xfail — see tests/conftest.py).  Remove the marker after the
+first green GPU run.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import neck_oracle as NO
+from golden_util import golden_files, load_neck_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.first_hw_run(reason="neck kernels: first hardware run pending (round-1 GPU budget spent)")]
+
+TOL = 5e-5     # fp32 summation order (K up to 2304) on O(1) GroupNorm outputs; the host emulation measures <= 1e-5
+CH = [96, 192, 384, 768]
+
+
+def make_engine(W, chans, stages=3):
+    from ddp_b200 import NeckEngine
+    eng = NeckEngine(chans, stages=stages)
+    eng.load_state_dict(W)
+    return eng
+
+
+@pytest.mark.parametrize("path", golden_files("neck"), ids=lambda p: os.path.basename(p)[:-4])
+def test_neck_matches_reference_golden(path):
+    W, xs, g = load_neck_case(path)
+    eng = make_engine(W, [x.shape[1] for x in xs])
+    x, fpn = eng.forward([t.cuda() for t in xs], want_fpn=True)
+    torch.cuda.synchronize()
+    for l, o in enumerate(fpn):
+        d = (o.cpu() - torch.from_numpy(g[f"fpn{l}"])).abs().max().item()
+        assert d < TOL, f"fpn level {l}: max|d| = {d:.3e}"
+    d = (x.cpu() - torch.from_numpy(g["out"])).abs().max().item()
+    assert d < TOL, f"x: max|d| = {d:.3e}"
+    assert eng.last_launch_count == 4 + 4 * 3 + 4 * (1 + 3 + 1) + 4 + 1 + 3 + 1
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 1, 1), (2, 5, 3), (1, 9, 17), (3, 4, 4), (2, 33, 65)])
+def test_neck_matches_oracle_on_ragged_shapes(B, h, w):
+    W = NO.make_weights(CH, seed=h * 31 + w)
+    xs = NO.make_inputs(CH, B, h, w, seed=7)
+    trace = {}
+    want = NO.neck(W, xs, trace)
+    x, fpn = make_engine(W, CH).forward([t.cuda() for t in xs], want_fpn=True)
+    for l, o in enumerate(fpn):
+        assert (o.cpu() - trace["fpn"][l]).abs().max().item() < TOL, f"fpn level {l}"
+    assert (x.cpu() - want).abs().max().item() < TOL
+
+
+def test_stage_split_equals_fused_and_batched_equals_per_image():
+    W = NO.make_weights(CH, seed=9)
+    xs = [t.cuda() for t in NO.make_inputs(CH, 3, 12, 20, seed=8)]
+    fused, fpn_fused = make_engine(W, CH, 3).forward(xs, want_fpn=True)
+    _, fpn_only = make_engine(W, CH, 1).forward(xs)
+    for a, b in zip(fpn_fused, fpn_only):
+        assert torch.equal(a, b)
+    merged, _ = make_engine(W, [256] * 4, 2).forward(fpn_only)
+    assert (merged - fused).abs().max().item() < 1e-5
+    # GroupNorm statistics are per image: a batched call equals per-image calls bit for bit
+    eng = make_engine(W, CH, 3)
+    for b in range(3):
+        one, _ = eng.forward([t[b:b + 1] for t in xs])
+        assert torch.equal(one, fused[b:b + 1])
+
+
+def test_cityscapes_shape_against_oracle():
+    """The headline geometry (128 x 256 tokens at level 0, Swin-T channels), one image, against the CPU oracle."""
+    W = NO.make_weights(CH, seed=41)
+    xs = NO.make_inputs(CH, 1, 128, 256, seed=42)
+    want = NO.neck(W, xs)
+    x, _ = make_engine(W, CH).forward([t.cuda() for t in xs])
+    d = (x.cpu() - want).abs()
+    assert d.max().item() < 1e-4, f"max|d| = {d.max().item():.3e}"
+    # size-independent property: every (image, group) of the GroupNorm output has the affine's statistics
+    y = (x - x.new_tensor(W["neck.1.down.gn.bias"].tolist()).view(1, -1, 1, 1)) / \
+        x.new_tensor(W["neck.1.down.gn.weight"].tolist()).view(1, -1, 1, 1)
+    yg = y.view(1, 32, -1)
+    assert yg.mean(-1).abs().max().item() < 1e-4 and (yg.var(-1, unbiased=False) - 1).abs().max().item() < 1e-3
+
+
+def test_plugin_fused_neck_feeds_the_decode_loop():
+    """neck=[FPN, MultiStageMerging] from a reference-style config -> FusedNeck -> x -> DDP.ddim_sample, vs oracles."""
+    import ddp_b200.models  # noqa: F401
+    from ddp_b200.neck import FusedNeck
+    from ddp_b200.registry import build_segmentor
+    from oracle import ddp_oracle as O
+    cfg = dict(type="DDP", timesteps=2, bit_scale=0.01, backbone=dict(type="NoSuchBackbone"),
+               neck=[dict(type="FPN", in_channels=CH, out_channels=256, act_cfg=None,
+                          norm_cfg=dict(type="GN", num_groups=32), num_outs=4),
+                     dict(type="MultiStageMerging", in_channels=[256] * 4, out_channels=256, kernel_size=1,
+                          norm_cfg=dict(type="GN", num_groups=32), act_cfg=None)],
+               decode_head=dict(type="DeformableHeadWithTime", in_channels=[256], channels=256, in_index=[0],
+                                dropout_ratio=0., num_classes=19, norm_cfg=dict(type="BN"), align_corners=False,
+                                num_feature_levels=1,
+                                encoder=dict(type="DetrTransformerEncoder", num_layers=6, transformerlayers=dict(
+                                    type="BaseTransformerLayer", use_time_mlp=True,
+                                    attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1,
+                                                   num_heads=8, dropout=0.),
+                                    ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, ffn_drop=0.,
+                                                  act_cfg=dict(type="GELU")),
+                                    operation_order=("self_attn", "norm", "ffn", "norm"))),
+                                positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True,
+                                                         offset=-0.5)),
+               test_cfg=dict(mode="whole"))
+    with pytest.warns(UserWarning):
+        model = build_segmentor(cfg)
+    assert isinstance(model.neck, FusedNeck)
+    ocfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    Wn, Wd = NO.make_weights(CH, seed=51), O.make_weights(ocfg, seed=52)
+    missing, unexpected = model.load_state_dict({**Wn, **Wd}, strict=False)
+    assert not unexpected and all(k.startswith(("backbone.", "auxiliary_head.")) for k in missing)
+    model = model.cuda().eval()
+    xs = NO.make_inputs(CH, 1, 12, 20, seed=53)
+    x = model.neck([t.cuda() for t in xs])
+    want_x = NO.neck(Wn, xs)
+    assert (x[0].cpu() - want_x).abs().max().item() < TOL
+    noise = torch.randn(1, 1, 256, 12, 20, generator=torch.Generator().manual_seed(54))
+    out = model.engine().sample(x[0], noise.cuda())
+    ref = O.sample(Wd, ocfg, want_x, noise)
+    assert (out.cpu() - ref).abs().max().item() < 5e-4
+    assert (out.cpu().argmax(1) != ref.argmax(1)).float().mean().item() < 2e-3
+
+
+def test_neck_error_behaviour():
+    from ddp_b200 import NeckEngine
+    from ddp_b200._lib import DDPError
+    with pytest.raises(DDPError, match="multiple of 16"):
+        NeckEngine([100, 192, 384, 768])
+    W = NO.make_weights(CH, seed=1)
+    eng = NeckEngine(CH)
+    with pytest.raises(DDPError, match="commit_weights"):
+        eng.forward([t.cuda() for t in NO.make_inputs(CH, 1, 4, 4, seed=1)])
+    with pytest.raises(KeyError):
+        eng.load_state_dict({k: v for k, v in W.items() if "down.gn" not in k})
+    eng.load_state_dict(W)
+    with pytest.raises(ValueError, match="expected"):
+        eng.forward([t.cuda() for t in NO.make_inputs([96, 192, 384, 512], 1, 4, 4, seed=1)])
+    x, _ = eng.forward([t.cuda() for t in NO.make_inputs(CH, 0, 4, 4, seed=1)])
+    assert tuple(x.shape) == (0, 256, 4, 4)
