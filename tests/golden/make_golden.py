@@ -3,6 +3,7 @@
     python tests/golden/make_golden.py seg
     python tests/golden/make_golden.py depth
     python tests/golden/make_golden.py neck
+    python tests/golden/make_golden.py bev
 
 Runs only in the build container (needs /root/reference).  It builds the
 reference's own classes from the reference's own config files
@@ -32,6 +33,7 @@ warnings.filterwarnings("ignore")
 import refshim  # noqa: E402
 from oracle import ddp_oracle as O  # noqa: E402
 from oracle import neck_oracle as NO  # noqa: E402
+from oracle import bev_oracle as BO  # noqa: E402
 
 SEG_CASES = [
     # name, config file, class override, num_classes, T, R, accumulation, h, w, wseed, xseed
@@ -265,5 +267,120 @@ def run_neck():
         print(case["name"], in_channels, tuple(out[0].shape), float(out[0].abs().mean()))
 
 
+# BEV map segmentation.  Scopes chosen so that the state grid is small: same structure as the shipped
+# grid_transform (input step 0.8, output step 0.5, output range inside the input range), fewer cells.
+BEV_CASES = [
+    dict(name="bev_camera_T3_R5", cfg="nuscenes/seg/ddp-camera-bev256d2-lss-scale001-d5-lr5e-5.yaml", T=None, R=None,
+         input_scope=((-6.4, 6.4, 0.8), (-8.0, 8.0, 0.8)), output_scope=((-6.0, 6.0, 0.5), (-7.5, 7.5, 0.5)),
+         wseed=41, xseed=401),
+    dict(name="bev_fusion_T2_R2", cfg="nuscenes/seg/ddp-fusion-bev256d2-lss-scale001-d5-lr5e-5.yaml", T=2, R=2,
+         input_scope=((-4.8, 4.8, 0.8), (-4.0, 4.0, 0.8)), output_scope=((-4.5, 4.5, 0.5), (-3.5, 3.5, 0.5)),
+         wseed=42, xseed=402),
+]
+
+
+def run_bev():
+    """bev/mmdet3d is not importable as a package here (its __init__ pulls compiled ops); load the two hot-path files
+    by path with the package context stubbed, exactly as written."""
+    import importlib.util
+    import yaml
+    refshim.install("segmentation")            # mmcv alias + the time-aware transformer layer fork (SURVEY fact 3)
+    import mmcv  # noqa: F401
+    import mmseg.models  # noqa: F401  registers BaseTransformerLayer(time), DetrTransformerEncoder, SinePositionalEncoding
+    from mmcv.utils import Registry
+    bev = f"{refshim.REF}/bev"
+
+    def pkg(name, path=None):
+        m = types.ModuleType(name)
+        m.__path__ = [path] if path else []
+        sys.modules[name] = m
+        return m
+    pkg("mmdet3d", f"{bev}/mmdet3d")
+    models = pkg("mmdet3d.models", f"{bev}/mmdet3d/models")
+    builder = types.ModuleType("mmdet3d.models.builder")
+    for n in ("build_backbone", "build_fuser", "build_head", "build_neck", "build_vtransform"):
+        setattr(builder, n, lambda *a, **k: None)
+    builder.HEADS = Registry("bev_heads")
+    builder.FUSIONMODELS = Registry("bev_fusion_models")
+    sys.modules["mmdet3d.models.builder"] = builder
+    models.FUSIONMODELS = builder.FUSIONMODELS
+    ops = pkg("mmdet3d.ops", f"{bev}/mmdet3d/ops")
+    ops.Voxelization = ops.DynamicScatter = object
+    spec = importlib.util.spec_from_file_location("mmdet3d.ops.norm", f"{bev}/mmdet3d/ops/norm.py")
+    norm = importlib.util.module_from_spec(spec)
+    sys.modules["mmdet3d.ops.norm"] = norm
+    spec.loader.exec_module(norm)               # the reference's own `resize`
+    pkg("mmdet3d.models.fusion_models", f"{bev}/mmdet3d/models/fusion_models")
+    bf = types.ModuleType("mmdet3d.models.fusion_models.bevfusion")
+
+    class BEVFusion(torch.nn.Module):           # the encoder side of the model never runs in ddim_sample
+        def __init__(self, **kw):
+            super().__init__()
+    bf.BEVFusion = BEVFusion
+    sys.modules["mmdet3d.models.fusion_models.bevfusion"] = bf
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    ddp_mod = load("mmdet3d.models.fusion_models.ddp", f"{bev}/mmdet3d/models/fusion_models/ddp.py")
+    head_mod = load("mmdet3d.models.heads.segm.deformable_head_with_time",
+                    f"{bev}/mmdet3d/models/heads/segm/deformable_head_with_time.py")
+    base = yaml.safe_load(open(f"{bev}/configs/nuscenes/default.yaml"))
+    for case in BEV_CASES:
+        y = yaml.safe_load(open(f"{bev}/configs/{case['cfg']}"))["model"]
+        from mmcv.utils import ConfigDict
+        hc = ConfigDict(y["heads"]["map"])                   # attribute access, as mmcv's Config gives the head
+        assert hc.pop("type") == "DeformableHeadWithTime"
+        T = case["T"] or y["timesteps"]
+        R = case["R"] or y["randsteps"]
+        head = head_mod.DeformableHeadWithTime(
+            classes=base["map_classes"], loss="focal",
+            grid_transform=dict(input_scope=[list(s) for s in case["input_scope"]],
+                                output_scope=[list(s) for s in case["output_scope"]]), **hc)
+        model = ddp_mod.DDP(bit_scale=y["bit_scale"], timesteps=T, randsteps=R, time_difference=y["time_difference"],
+                            learned_sinusoidal_dim=y["learned_sinusoidal_dim"], sample_range=tuple(y["sample_range"]),
+                            noise_schedule=y["noise_schedule"], diffusion=y["diffusion"],
+                            **({"feat_channels": y["feat_channels"]} if "feat_channels" in y else {}))
+        feat = model.transform.conv.in_channels - 256
+        model.heads = torch.nn.ModuleDict({"map": head})
+        model.eval()
+        bcfg = BO.BevConfig(timesteps=T, randsteps=R, time_difference=y["time_difference"], bit_scale=y["bit_scale"],
+                            num_layers=hc["encoder"]["num_layers"], feat_channels=feat,
+                            input_scope=case["input_scope"], output_scope=case["output_scope"])
+        W = BO.make_weights(bcfg, seed=case["wseed"])
+        sd = model.state_dict()
+        assert sorted(sd) == sorted(W), (sorted(set(sd) ^ set(W)))
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(W[k].shape), k
+        model.load_state_dict(W)
+        h = len(torch.arange(*case["input_scope"][0]))
+        w = len(torch.arange(*case["input_scope"][1]))
+        x = torch.randn(1, feat, h, w, generator=torch.Generator().manual_seed(case["xseed"]))
+        nseed = case["xseed"] + 1000
+        torch.manual_seed(nseed)
+        noise = torch.randn((R, 256, h, w))              # what fusion_models/ddp.py:275 will draw
+        steps = []
+        orig = head.forward
+
+        def wrapped(inputs, times, target=None, _orig=orig, _steps=steps):
+            out = _orig(inputs, times, target)
+            _steps.append(out.detach().clone())
+            return out
+        head.forward = wrapped
+        torch.manual_seed(nseed)
+        out = model.ddim_sample([x], head)
+        np.savez_compressed(
+            os.path.join(HERE, case["name"] + ".npz"),
+            task="bev", config=case["cfg"], timesteps=T, randsteps=R, bit_scale=bcfg.bit_scale,
+            num_layers=bcfg.num_layers, feat_channels=feat, input_scope=np.array(case["input_scope"]), output_scope=np.array(case["output_scope"]),
+            h=h, w=w, wseed=case["wseed"], xseed=case["xseed"], nseed=nseed, x_checksum=checksum(x),
+            noise_checksum=checksum(noise), w_checksum=checksum(torch.cat([v.flatten() for _, v in sorted(W.items())])),
+            out=out.numpy(), step_prob=torch.stack(steps).numpy().astype(np.float32))
+        print(case["name"], (h, w), tuple(out.shape), float(out.mean()), float((out > 0.5).float().mean()))
+
+
 if __name__ == "__main__":
-    {"seg": run_seg, "depth": run_depth, "neck": run_neck}[sys.argv[1]]()
+    {"seg": run_seg, "depth": run_depth, "neck": run_neck, "bev": run_bev}[sys.argv[1]]()

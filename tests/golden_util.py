@@ -7,6 +7,7 @@ import torch
 
 from oracle import ddp_oracle as O
 from oracle import neck_oracle as NO
+from oracle import bev_oracle as BO
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -72,3 +73,25 @@ def load_neck_case(path):
     wsum = checksum(torch.cat([v.flatten() for _, v in sorted(W.items())]))
     assert np.allclose(wsum, g["w_checksum"], rtol=0, atol=1e-5), "weight regeneration drifted"
     return W, xs, g
+
+
+def load_bev_case(path):
+    """-> (cfg, W, x (1,feat,h,w), noise (R,256,h,w), golden dict) of a bev_*.npz fixture."""
+    g = dict(np.load(path, allow_pickle=False))
+    assert str(g["task"]) == "bev"
+    cfg = BO.BevConfig(timesteps=int(g["timesteps"]), randsteps=int(g["randsteps"]), bit_scale=float(g["bit_scale"]),
+                       num_layers=int(g["num_layers"]), feat_channels=int(g["feat_channels"]),
+                       input_scope=tuple(tuple(float(v) for v in r) for r in g["input_scope"]),
+                       output_scope=tuple(tuple(float(v) for v in r) for r in g["output_scope"]))
+    W = BO.make_weights(cfg, seed=int(g["wseed"]))
+    h, w = int(g["h"]), int(g["w"])
+    x = torch.randn(1, cfg.feat_channels, h, w, generator=torch.Generator().manual_seed(int(g["xseed"])))
+    state = torch.get_rng_state()
+    torch.manual_seed(int(g["nseed"]))
+    noise = torch.randn((cfg.randsteps, 256, h, w))
+    torch.set_rng_state(state)
+    assert np.allclose(checksum(x), g["x_checksum"], rtol=0, atol=1e-6), "x regeneration drifted"
+    assert np.allclose(checksum(noise), g["noise_checksum"], rtol=0, atol=1e-6), "noise regeneration drifted"
+    wsum = checksum(torch.cat([v.flatten() for _, v in sorted(W.items())]))
+    assert np.allclose(wsum, g["w_checksum"], rtol=0, atol=1e-5), "weight regeneration drifted"
+    return cfg, W, x, noise, g

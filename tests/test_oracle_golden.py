@@ -8,7 +8,8 @@ import torch
 
 from oracle import ddp_oracle as O
 from oracle import neck_oracle as NO
-from golden_util import golden_files, load_case, load_neck_case
+from oracle import bev_oracle as BO
+from golden_util import golden_files, load_case, load_neck_case, load_bev_case
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
@@ -137,3 +138,25 @@ def test_neck_merge_commutes_with_the_1x1_conv():
     got = F.group_norm(pre, NO.GROUPS, W["neck.1.down.gn.weight"], W["neck.1.down.gn.bias"], NO.EPS)
     want = NO.multi_stage_merging(W, outs)
     assert (got - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("path", golden_files("bev"), ids=lambda p: os.path.basename(p)[:-4])
+def test_bev_oracle_matches_reference_output(path):
+    """BEV ddim_sample + head restatement vs the unmodified reference classes (make_golden.py bev)."""
+    cfg, W, x, noise, g = load_bev_case(path)
+    ref = torch.from_numpy(g["out"])
+    trace = {}
+    out = BO.ddim_sample_bev(W, cfg, x, noise, trace)
+    assert out.shape == ref.shape
+    d = (out - ref).abs().max().item()
+    assert d < 2e-5, f"max |d| = {d:.3e}"          # plain tensors: matmul folding differs from nn.Parameter weights
+    steps = torch.stack(trace["prob"])
+    want = torch.from_numpy(g["step_prob"])
+    assert (steps - want).abs().max().item() < 2e-5
+    # the thresholded multi-hot maps (what feeds back into the state) agree everywhere outside fp32 ties at 0.5
+    flips = (steps > cfg.threshold) != (want > cfg.threshold)
+    assert int(flips.sum()) == 0 or float((want[flips] - cfg.threshold).abs().max()) < 1e-5
+    Wp = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    with torch.no_grad():
+        out_p = BO.ddim_sample_bev(Wp, cfg, x, noise)
+    assert torch.equal(out_p, ref), f"max |d| = {(out_p - ref).abs().max().item():.3e}"   # same ops, same order: bit-for-bit
