@@ -26,7 +26,10 @@ EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "dd
            "ddp_profile_collect", "ddp_kernel_class_name",
            "ddp_neck_create", "ddp_neck_destroy", "ddp_neck_last_error", "ddp_neck_weight_count", "ddp_neck_weight_name",
            "ddp_neck_set_weight", "ddp_neck_commit_weights", "ddp_neck_plan", "ddp_neck_forward",
-           "ddp_neck_last_launch_count"]
+           "ddp_neck_last_launch_count",
+           "ddp_bev_create", "ddp_bev_destroy", "ddp_bev_last_error", "ddp_bev_weight_count", "ddp_bev_weight_name",
+           "ddp_bev_set_weight", "ddp_bev_commit_weights", "ddp_bev_set_schedule", "ddp_bev_plan", "ddp_bev_sample",
+           "ddp_bev_last_launch_count"]
 NECK_STAGE_FPN, NECK_STAGE_MERGE = 1, 2
 K_COUNT = 14
 
@@ -45,6 +48,14 @@ class DDPNeckConfig(ctypes.Structure):
     _fields_ = [("abi_version", ctypes.c_int32), ("stages", ctypes.c_int32), ("num_levels", ctypes.c_int32),
                 ("in_channels", ctypes.c_int32 * 4), ("out_channels", ctypes.c_int32), ("num_groups", ctypes.c_int32),
                 ("eps", ctypes.c_float)]
+
+
+class DDPBevConfig(ctypes.Structure):
+    _fields_ = [("abi_version", ctypes.c_int32), ("timesteps", ctypes.c_int32), ("time_difference", ctypes.c_int32),
+                ("noise_schedule", ctypes.c_int32), ("diffusion", ctypes.c_int32),
+                ("learned_sinusoidal_dim", ctypes.c_int32), ("num_layers", ctypes.c_int32),
+                ("feat_channels", ctypes.c_int32), ("gemm_mode", ctypes.c_int32), ("bit_scale", ctypes.c_float),
+                ("threshold", ctypes.c_float)]
 
 
 class DDPError(RuntimeError):
@@ -112,6 +123,21 @@ def load():
     lib.ddp_neck_forward.argtypes = [vp, ctypes.POINTER(vp), vp, ctypes.POINTER(vp), vp, ctypes.c_size_t, vp]
     lib.ddp_neck_last_launch_count.argtypes = [vp]
     lib.ddp_neck_last_launch_count.restype = i64
+    lib.ddp_bev_create.argtypes = [ctypes.POINTER(DDPBevConfig), ctypes.POINTER(vp)]
+    lib.ddp_bev_destroy.argtypes = [vp]
+    lib.ddp_bev_destroy.restype = None
+    lib.ddp_bev_last_error.argtypes = [vp]
+    lib.ddp_bev_last_error.restype = cp
+    lib.ddp_bev_weight_count.argtypes = [vp]
+    lib.ddp_bev_weight_name.argtypes = [vp, i32, ctypes.POINTER(i64)]
+    lib.ddp_bev_weight_name.restype = cp
+    lib.ddp_bev_set_weight.argtypes = [vp, cp, vp, i64]
+    lib.ddp_bev_commit_weights.argtypes = [vp]
+    lib.ddp_bev_set_schedule.argtypes = [vp, i32, fp, fp, fp, fp, fp]
+    lib.ddp_bev_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, fp, fp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.ddp_bev_sample.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    lib.ddp_bev_last_launch_count.argtypes = [vp]
+    lib.ddp_bev_last_launch_count.restype = i64
     if lib.ddp_abi_version() != ABI_VERSION:
         raise ImportError(f"libddp_b200.so ABI {lib.ddp_abi_version()} != binding {ABI_VERSION}; rebuild")
     _lib = lib

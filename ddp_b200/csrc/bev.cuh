@@ -1,0 +1,287 @@
+// CUDA backend + C ABI of the BEV map-segmentation variant of the decode loop — SURVEY 8f #4.
+// The launch sequence and the per-element kernel bodies live in bev_plan.h (shared with the host emulation the CPU
+// tests use).  The denoiser is NOT re-implemented: a ddp_bev owns an inner segmentation ddp_handle (6 classes,
+// num_layers = 5, planned on the OUTPUT grid) and calls the hardware-verified ddp_head_forward once per step, with the
+// step's time embedding taken from the inner handle's precomputed table.
+//
+// Included at the end of ddp_b200.cu (same translation unit: it reaches into ddp_handle).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/ddp_b200.h"
+#include "bev_plan.h"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+#include "neck.cuh"          // k_for_each
+
+struct ddp_bev {
+    ddp_bev_config cfg;
+    int device = 0;
+    std::string err;
+    ddp_handle* inner = nullptr;
+    std::vector<float> tr_w, tr_b, emb;      // host copies of transform.conv.{weight,bias}, embedding_table.weight
+    bool have_tr_w = false, have_tr_b = false, have_emb = false, committed = false, planned = false;
+    std::vector<std::string> names;          // reference state-dict keys, index-aligned with `numels`
+    std::vector<int64_t> numels;
+    float* w_arena = nullptr;                // wx_t | wm_t | b_tr | emb
+    float* g_arena = nullptr;                // grid_y | grid_x
+    ddp::bev::Weights w{};
+    ddp::bev::Dims dims{};
+    size_t own_bytes = 0, ws_bytes = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+std::string g_bev_create_err;
+
+int bfail(ddp_bev* h, int code, const char* fmt, ...) {
+    char buf[640];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_bev_create_err = buf;
+    return code;
+}
+
+#define BEV_CUDA_TRY(h, expr)                                                                     \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return bfail(h, DDP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                         __FILE__, __LINE__);                                                     \
+    } while (0)
+
+// reference key of the BEV model -> key of the inner segmentation handle ("" = not forwarded)
+std::string bev_inner_key(const std::string& k) {
+    const std::string hp = "heads.map.";
+    if (k.compare(0, hp.size(), hp) == 0) return "decode_head." + k.substr(hp.size());
+    if (k == "transform.conv.weight" || k == "transform.conv.bias") return "";
+    return k;                                   // embedding_table.weight, time_mlp.*
+}
+
+struct BevCudaBackend {
+    ddp_bev* h;
+    void* inner_ws;
+    cudaStream_t st;
+    int64_t launches = 0;
+
+    template <class F>
+    void for_each(size_t n, const F& f) {
+        if (n == 0) return;
+        ddp::neck::k_for_each<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n);
+        ++launches;
+    }
+    void gemm_cond(const float* x, int feat, int N, int B, const float* wx_t, const float* bias, float* cond) {
+        ddp::EpiBias epi{cond, bias, ddp::kE, ddp::kE, B * N};
+        ddp::launch_gemm_simt<256, 1>(x, 0, N, wx_t, ddp::kE, B * N, feat, ddp::kE, epi, st);
+        ++launches;
+    }
+    void gemm_head_in(const float* state, const float* wm_t, const float* cond, int N, int R, int rows, float* q) {
+        ddp::EpiAddCond epi{q, cond, N, R, rows * N};
+        ddp::launch_gemm_simt<256, 0>(state, ddp::kE, 0, wm_t, ddp::kE, rows * N, ddp::kE, ddp::kE, epi, st);
+        ++launches;
+    }
+    void nchw_to_tokens(const float* src, float* dst, int imgs, int C, int N) {
+        dim3 grid((N + 31) / 32, (C + 31) / 32, imgs);
+        ddp::k_nchw_to_tokens<<<grid, dim3(32, 8), 0, st>>>(src, dst, C, N);
+        ++launches;
+    }
+    void tokens_to_nchw(const float* src, float* dst, int imgs, int N, int C) {     // same kernel, roles swapped
+        dim3 grid((C + 31) / 32, (N + 31) / 32, imgs);
+        ddp::k_nchw_to_tokens<<<grid, dim3(32, 8), 0, st>>>(src, dst, N, C);
+        ++launches;
+    }
+    int denoise(int k, const float* feat_nchw, float* logits) {
+        ddp_handle* in = h->inner;
+        const int rc = ddp_head_forward(in, feat_nchw, in->temb + (size_t)k * ddp::kTimeDim, logits, inner_ws,
+                                        in->ws_compute_bytes, st);
+        if (rc) return bfail(h, rc, "denoiser (ddp_head_forward) failed at step %d: %s", k, ddp_last_error(in));
+        launches += in->launches;
+        return 0;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* ddp_bev_last_error(const ddp_bev* h) { return h ? h->err.c_str() : g_bev_create_err.c_str(); }
+
+int ddp_bev_create(const ddp_bev_config* cfg, ddp_bev** out) {
+    if (!cfg || !out) return bfail(nullptr, DDP_ERR_INVALID, "ddp_bev_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != DDP_ABI_VERSION)
+        return bfail(nullptr, DDP_ERR_INVALID, "ddp_bev_create: abi_version %d != %d", cfg->abi_version, DDP_ABI_VERSION);
+    if (cfg->feat_channels < 16 || cfg->feat_channels % 16)
+        return bfail(nullptr, DDP_ERR_UNSUPPORTED, "ddp_bev_create: feat_channels %d must be a positive multiple of 16", cfg->feat_channels);
+    if (cfg->noise_schedule != DDP_SCHEDULE_COSINE && cfg->noise_schedule != DDP_SCHEDULE_LINEAR)
+        return bfail(nullptr, DDP_ERR_INVALID, "invalid noise schedule %d", cfg->noise_schedule);        // fusion_models/ddp.py:102 ValueError
+    if (cfg->diffusion != DDP_DIFFUSION_DDIM)   // the reference's BEV ddpm_sample indexes a (r b) tensor with [0] and embeds floats: it cannot run
+        return bfail(nullptr, DDP_ERR_UNSUPPORTED, "ddp_bev_create: only diffusion='ddim' is built for the BEV variant");
+    ddp_config ic{};
+    ic.abi_version = DDP_ABI_VERSION; ic.task = DDP_TASK_SEG; ic.num_classes = ddp::bev::kClasses;
+    ic.timesteps = cfg->timesteps; ic.time_difference = cfg->time_difference; ic.noise_schedule = cfg->noise_schedule;
+    ic.diffusion = DDP_DIFFUSION_DDIM; ic.accumulation = 0; ic.learned_sinusoidal_dim = cfg->learned_sinusoidal_dim;
+    ic.num_layers = cfg->num_layers; ic.gemm_mode = cfg->gemm_mode; ic.sample_range_lo = 0.f; ic.bit_scale = cfg->bit_scale;
+    ddp_handle* inner = nullptr;
+    const int rc = ddp_create(&ic, &inner);
+    if (rc) return bfail(nullptr, rc, "ddp_bev_create: %s", ddp_last_error(nullptr));
+    ddp_bev* h = new ddp_bev();
+    h->cfg = *cfg;
+    h->device = inner->device;
+    h->inner = inner;
+    // reference keys: the inner handle's list with decode_head.* renamed and the transform resized to feat_channels
+    for (const auto& s : inner->specs) {
+        std::string k = s.name;
+        int64_t n = s.numel;
+        const std::string dh = "decode_head.";
+        if (k.compare(0, dh.size(), dh) == 0) k = "heads.map." + k.substr(dh.size());
+        if (k == "transform.conv.weight") n = (int64_t)ddp::kE * (cfg->feat_channels + ddp::kE);
+        h->names.push_back(k);
+        h->numels.push_back(n);
+    }
+    *out = h;
+    return DDP_OK;
+}
+
+void ddp_bev_destroy(ddp_bev* h) {
+    if (!h) return;
+    if (h->inner) ddp_destroy(h->inner);
+    if (h->w_arena) cudaFree(h->w_arena);
+    if (h->g_arena) cudaFree(h->g_arena);
+    delete h;
+}
+
+int ddp_bev_weight_count(const ddp_bev* h) { return h ? (int)h->names.size() : 0; }
+
+const char* ddp_bev_weight_name(const ddp_bev* h, int index, int64_t* numel) {
+    if (!h || index < 0 || index >= (int)h->names.size()) return nullptr;
+    if (numel) *numel = h->numels[index];
+    return h->names[index].c_str();
+}
+
+int ddp_bev_set_weight(ddp_bev* h, const char* name, const float* host_data, int64_t numel) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!name || !host_data) return bfail(h, DDP_ERR_INVALID, "ddp_bev_set_weight: null argument");
+    const std::string k = name;
+    size_t i = 0;
+    while (i < h->names.size() && h->names[i] != k) ++i;
+    if (i == h->names.size()) return bfail(h, DDP_ERR_WEIGHT, "ddp_bev_set_weight: '%s' is not a weight of the BEV decode path", name);
+    if (numel != h->numels[i])
+        return bfail(h, DDP_ERR_WEIGHT, "ddp_bev_set_weight: '%s' has %lld elements, expected %lld", name, (long long)numel,
+                     (long long)h->numels[i]);
+    h->committed = false;
+    if (k == "transform.conv.weight") { h->tr_w.assign(host_data, host_data + numel); h->have_tr_w = true; return DDP_OK; }
+    if (k == "transform.conv.bias") { h->tr_b.assign(host_data, host_data + numel); h->have_tr_b = true; return DDP_OK; }
+    if (k == "embedding_table.weight") { h->emb.assign(host_data, host_data + numel); h->have_emb = true; }
+    const int rc = ddp_set_weight(h->inner, bev_inner_key(k).c_str(), host_data, numel);
+    if (rc) return bfail(h, rc, "ddp_bev_set_weight: %s", ddp_last_error(h->inner));
+    return DDP_OK;
+}
+
+int ddp_bev_commit_weights(ddp_bev* h) {
+    using namespace ddp::bev;
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->have_tr_w || !h->have_tr_b || !h->have_emb)
+        return bfail(h, DDP_ERR_STATE, "ddp_bev_commit_weights: transform.conv.{weight,bias} / embedding_table.weight were never set");
+    // the inner handle's own transform (256 x 512) is never used by ddp_head_forward: the BEV transform runs here
+    {
+        std::vector<float> zeros((size_t)ddp::kE * 2 * ddp::kE, 0.f);
+        int rc = ddp_set_weight(h->inner, "transform.conv.weight", zeros.data(), (int64_t)zeros.size());
+        if (!rc) rc = ddp_set_weight(h->inner, "transform.conv.bias", zeros.data(), ddp::kE);
+        if (!rc) rc = ddp_commit_weights(h->inner);
+        if (rc) return bfail(h, rc, "ddp_bev_commit_weights: %s", ddp_last_error(h->inner));
+    }
+    const int feat = h->cfg.feat_channels;
+    std::vector<float> wx = ddp::neck::repack_1x1(h->tr_w.data(), ddp::kE, feat + ddp::kE, 0, feat);
+    std::vector<float> wm = ddp::neck::repack_1x1(h->tr_w.data(), ddp::kE, feat + ddp::kE, feat, ddp::kE);
+    std::vector<float> arena;
+    std::vector<size_t> offs;
+    for (const std::vector<float>* v : {&wx, &wm, &h->tr_b, &h->emb}) {
+        offs.push_back(arena.size());
+        arena.insert(arena.end(), v->begin(), v->end());
+        arena.resize((arena.size() + 63) / 64 * 64);
+    }
+    BEV_CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->w_arena) { cudaFree(h->w_arena); h->w_arena = nullptr; }
+    BEV_CUDA_TRY(h, cudaMalloc(&h->w_arena, arena.size() * sizeof(float)));
+    BEV_CUDA_TRY(h, cudaMemcpy(h->w_arena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->w.wx_t = h->w_arena + offs[0];
+    h->w.wm_t = h->w_arena + offs[1];
+    h->w.b_tr = h->w_arena + offs[2];
+    h->w.emb = h->w_arena + offs[3];
+    h->committed = true;
+    h->planned = false;
+    return DDP_OK;
+}
+
+int ddp_bev_set_schedule(ddp_bev* h, int timesteps, const float* time_in, const float* a_now, const float* s_now,
+                         const float* a_next, const float* s_next) {
+    if (!h) return DDP_ERR_INVALID;
+    const int rc = ddp_set_schedule(h->inner, timesteps, time_in, a_now, s_now, a_next, s_next);
+    if (rc) return bfail(h, rc, "ddp_bev_set_schedule: %s", ddp_last_error(h->inner));
+    return DDP_OK;
+}
+
+int ddp_bev_plan(ddp_bev* h, int B, int R, int in_h, int in_w, int out_h, int out_w, const float* grid_y, const float* grid_x,
+                 size_t* workspace_bytes) {
+    using namespace ddp::bev;
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->committed) return bfail(h, DDP_ERR_STATE, "ddp_bev_plan: call ddp_bev_commit_weights first");
+    if (!grid_y || !grid_x) return bfail(h, DDP_ERR_INVALID, "ddp_bev_plan: null grid");
+    if (B < 1 || R < 1 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1 || B * (long long)R > 65535)
+        return bfail(h, DDP_ERR_INVALID, "ddp_bev_plan: B, R, grid sizes must be >= 1 (B * R <= 65535)");
+    if ((long long)B * R * in_h * in_w > (1LL << 23) || (long long)B * R * out_h * out_w > (1LL << 23))
+        return bfail(h, DDP_ERR_UNSUPPORTED, "ddp_bev_plan: more than 2^23 tokens in flight");   // 32-bit element counts x 256 channels
+    size_t inner_bytes = 0;
+    const int rc = ddp_plan(h->inner, B, R, out_h, out_w, &inner_bytes);       // the denoiser runs on the output grid
+    if (rc) return bfail(h, rc, "ddp_bev_plan: %s", ddp_last_error(h->inner));
+    BEV_CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->g_arena) { cudaFree(h->g_arena); h->g_arena = nullptr; }
+    BEV_CUDA_TRY(h, cudaMalloc(&h->g_arena, (size_t)(out_h + out_w) * sizeof(float)));
+    BEV_CUDA_TRY(h, cudaMemcpy(h->g_arena, grid_y, out_h * sizeof(float), cudaMemcpyHostToDevice));
+    BEV_CUDA_TRY(h, cudaMemcpy(h->g_arena + out_h, grid_x, out_w * sizeof(float), cudaMemcpyHostToDevice));
+    h->w.grid_y = h->g_arena;
+    h->w.grid_x = h->g_arena + out_h;
+    Dims d{B, R, h->cfg.timesteps, h->cfg.feat_channels, in_h, in_w, out_h, out_w, h->cfg.bit_scale, h->cfg.threshold};
+    h->dims = d;
+    h->own_bytes = carve(d, nullptr, nullptr);
+    h->ws_bytes = h->own_bytes + (h->inner->ws_compute_bytes + 255) / 256 * 256;
+    h->planned = true;
+    if (workspace_bytes) *workspace_bytes = h->ws_bytes;
+    return DDP_OK;
+}
+
+int ddp_bev_sample(ddp_bev* h, const float* x, const float* noise, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    using namespace ddp::bev;
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->planned) return bfail(h, DDP_ERR_STATE, "ddp_bev_sample: call ddp_bev_plan first");
+    if (!x || !noise || !out || !workspace) return bfail(h, DDP_ERR_INVALID, "ddp_bev_sample: null pointer");
+    if (workspace_bytes < h->ws_bytes)
+        return bfail(h, DDP_ERR_WORKSPACE, "ddp_bev_sample: workspace %zu < required %zu", workspace_bytes, h->ws_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return bfail(h, DDP_ERR_WORKSPACE, "ddp_bev_sample: workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ddp_handle* in = h->inner;
+    if (in->time_dirty) {          // schedule changed after the plan: refresh the per-step time embeddings
+        const int rc = compute_time_constants(in, st);
+        if (rc) return bfail(h, rc, "ddp_bev_sample: %s", ddp_last_error(in));
+    }
+    Buffers buf;
+    carve(h->dims, static_cast<char*>(workspace), &buf);
+    BevCudaBackend be{h, static_cast<char*>(workspace) + h->own_bytes, st};
+    Schedule sch{in->a_now.data(), in->s_now.data(), in->a_next.data(), in->s_next.data()};
+    const int rc = bev_run(be, h->dims, h->w, sch, buf, x, noise, out);
+    h->launches = be.launches;
+    if (rc) return rc;
+    BEV_CUDA_TRY(h, cudaGetLastError());
+    return DDP_OK;
+}
+
+int64_t ddp_bev_last_launch_count(const ddp_bev* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

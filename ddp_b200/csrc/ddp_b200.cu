@@ -1258,3 +1258,6 @@ int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host,
 
 // The neck in front of the loop (FPN + MultiStageMerging): its own handle type and entry points.
 #include "neck.cuh"
+
+// The BEV map-segmentation variant of the loop: a handle around an inner segmentation handle.
+#include "bev.cuh"

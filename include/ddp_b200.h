@@ -245,6 +245,65 @@ int ddp_neck_forward(ddp_neck* h, const float* const* inputs, float* x_out, floa
                      size_t workspace_bytes, void* stream);
 int64_t ddp_neck_last_launch_count(const ddp_neck* h);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * BEV map segmentation: the same denoiser inside the BEV tree's sampling loop.
+ *
+ * Reference interfaces replaced (paths relative to bev/):
+ *   ddp_bev_create / set_weight    DDP.__init__                    mmdet3d/models/fusion_models/ddp.py:65-116
+ *                                  DeformableHeadWithTime.__init__ mmdet3d/models/heads/segm/deformable_head_with_time.py:109-142
+ *   ddp_bev_plan                   BEVGridTransform                mmdet3d/models/heads/segm/deformable_head_with_time.py:58-98
+ *   ddp_bev_sample                 DDP.ddim_sample                 mmdet3d/models/fusion_models/ddp.py:268-301
+ *                                  (calls DeformableHeadWithTime.forward, heads/segm/deformable_head_with_time.py:178-241)
+ * Two token grids: the state m_t lives on the fused BEV feature grid (in_h x in_w), the denoiser runs on the output map
+ * grid (out_h x out_w) after a bilinear grid_sample; 6 sigmoid classes thresholded at `threshold`; the result is the mean
+ * of the sigmoid maps over all timesteps * randsteps evaluations.  The reference's ddpm_sample for this model cannot
+ * run (it indexes the repeated feature with [0] and feeds floats to nn.Embedding, ddp.py:303-342): only ddim is built.
+ * Same conventions as ddp_sample (caller-owned device memory, asynchronous on `stream`, status codes, no CPU path).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ddp_bev ddp_bev;
+
+typedef struct ddp_bev_config {
+    int32_t abi_version;            /* DDP_ABI_VERSION */
+    int32_t timesteps;              /* DDP(timesteps=) */
+    int32_t time_difference;        /* DDP(time_difference=) */
+    int32_t noise_schedule;         /* DDP_SCHEDULE_* */
+    int32_t diffusion;              /* DDP_DIFFUSION_DDIM */
+    int32_t learned_sinusoidal_dim; /* 16 */
+    int32_t num_layers;             /* heads.map.encoder.num_layers, 5 in the shipped configs */
+    int32_t feat_channels;          /* DDP(feat_channels=): 256 camera-only, 512 (default) fusion */
+    int32_t gemm_mode;              /* DDP_GEMM_* of the denoiser */
+    float   bit_scale;              /* DDP(bit_scale=) */
+    float   threshold;              /* DDP(threshold=), 0.5 */
+} ddp_bev_config;
+
+int ddp_bev_create(const ddp_bev_config* cfg, ddp_bev** out);
+void ddp_bev_destroy(ddp_bev* h);
+const char* ddp_bev_last_error(const ddp_bev* h);     /* h may be NULL: last create error */
+
+/* Weights by the BEV model's state-dict keys: embedding_table.weight (7,256), transform.conv.weight
+ * (256, feat_channels + 256, 1, 1), transform.conv.bias, time_mlp.*, heads.map.encoder.layers.N.*, heads.map.conv_seg.*. */
+int ddp_bev_weight_count(const ddp_bev* h);
+const char* ddp_bev_weight_name(const ddp_bev* h, int index, int64_t* numel);
+int ddp_bev_set_weight(ddp_bev* h, const char* name, const float* host_data, int64_t numel);
+int ddp_bev_commit_weights(ddp_bev* h);
+
+/* Optional schedule override, same meaning as ddp_set_schedule (seg). */
+int ddp_bev_set_schedule(ddp_bev* h, int timesteps, const float* time_in, const float* a_now, const float* s_now,
+                         const float* a_next, const float* s_next);
+
+/* Geometry.  grid_y [out_h] / grid_x [out_w]: HOST arrays of the normalised ([-1, 1]) sampling coordinates
+ * BEVGridTransform computes from its input_scope / output_scope (deformable_head_with_time.py:82-88); the host computes
+ * them with the reference's own ops so that they are bit-identical to a reference run. */
+int ddp_bev_plan(ddp_bev* h, int B, int R, int in_h, int in_w, int out_h, int out_w, const float* grid_y, const float* grid_x,
+                 size_t* workspace_bytes);
+
+/*   x      (B,feat_channels,in_h,in_w) fp32 NCHW device    fused BEV feature (decoder neck output)
+ *   noise  (B,R,256,in_h,in_w) fp32 device                  initial state (ddp.py:275 draws it; here the caller does)
+ *   out    (B,6,out_h,out_w) fp32 device                    mean sigmoid map */
+int ddp_bev_sample(ddp_bev* h, const float* x, const float* noise, float* out, void* workspace, size_t workspace_bytes,
+                   void* stream);
+int64_t ddp_bev_last_launch_count(const ddp_bev* h);
+
 #ifdef __cplusplus
 }
 #endif

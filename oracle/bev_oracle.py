@@ -79,13 +79,25 @@ def grid_transform(x, input_scope, output_scope):
     return F.grid_sample(x, grid, mode="bilinear", align_corners=False)
 
 
-def head_bev(W, cfg: BevConfig, feat, time):
+def head_bev(W, cfg: BevConfig, feat, time, trace=None):
     """feat (rows, 256, h, w), time (1, 1024) -> sigmoid maps (rows, 6, H', W') on the output grid."""
     Ws = _as_seg_keys(W)
     feat = grid_transform(feat, cfg.input_scope, cfg.output_scope)
     mem = O.head_tokens(Ws, cfg.seg_config(), feat, time)
     x = F.conv2d(mem, Ws["decode_head.conv_seg.weight"], Ws["decode_head.conv_seg.bias"])
+    if trace is not None:
+        trace.setdefault("feat_grid", []).append(feat)
+        trace.setdefault("logit", []).append(x)
     return torch.sigmoid(x)
+
+
+def grid_coords(input_scope, output_scope):
+    """The normalised sampling coordinates of BEVGridTransform (rows, columns) — deformable_head_with_time.py:82-88."""
+    coords = []
+    for (imin, imax, _), (omin, omax, ostep) in zip(input_scope, output_scope):
+        v = torch.arange(omin + ostep / 2, omax, ostep)
+        coords.append((v - imin) / (imax - imin) * 2 - 1)
+    return coords
 
 
 def ddim_sample_bev(W, cfg: BevConfig, x, noise, trace=None):
@@ -104,7 +116,7 @@ def ddim_sample_bev(W, cfg: BevConfig, x, noise, trace=None):
         alpha, sigma = O.alpha_sigma(log_snr.view(1, 1, 1, 1))
         alpha_next, sigma_next = O.alpha_sigma(log_snr_next.view(1, 1, 1, 1))
         temb = O.time_mlp(W, log_snr)
-        prob = head_bev(W, cfg, feat, temb)
+        prob = head_bev(W, cfg, feat, temb, trace)
         pred = (prob > cfg.threshold)
         factor = (torch.arange(NUM_CLASSES) + 1).view(1, NUM_CLASSES, 1, 1)
         pred = pred * factor
@@ -115,6 +127,7 @@ def ddim_sample_bev(W, cfg: BevConfig, x, noise, trace=None):
         mask_t = pred * alpha_next + eps * sigma_next
         outs.append(prob)
         if trace is not None:
+            trace.setdefault("feat", []).append(feat)
             trace.setdefault("prob", []).append(prob)
             trace.setdefault("mask_t", []).append(mask_t)
     return torch.cat(outs, dim=0).mean(dim=0, keepdim=True)

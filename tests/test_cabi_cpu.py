@@ -55,6 +55,17 @@ def test_neck_binding_struct_matches_header():
         assert cty is base if not arr else (cty._type_ is base and cty._length_ == int(arr[1:-1]))
 
 
+def test_bev_binding_struct_matches_header():
+    from ddp_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "ddp_b200.h")).read()
+    body = re.search(r"typedef struct ddp_bev_config \{(.*?)\} ddp_bev_config;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"(int32_t|float)\s+([a-z_]+);", body)
+    assert [f for _, f in fields] == [n for n, _ in _lib.DDPBevConfig._fields_]
+    for (ty, _), (_, cty) in zip(fields, _lib.DDPBevConfig._fields_):
+        assert cty is (ctypes.c_int32 if ty == "int32_t" else ctypes.c_float)
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():

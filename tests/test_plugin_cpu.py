@@ -114,6 +114,69 @@ def test_neck_plugin_surface():
             fpn([torch.zeros(1, c, 4, 4) for c in (96, 192, 384, 768)])
 
 
+def _bev_head_cfg(scopes):
+    return dict(type="DeformableHeadWithTime", in_channels=256, num_feature_levels=1,
+                encoder=dict(type="DetrTransformerEncoder", num_layers=5, transformerlayers=dict(
+                    type="BaseTransformerLayer", use_time_mlp=True,
+                    attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1, num_heads=8, dropout=0.0),
+                    ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                                  act_cfg=dict(type="GELU"), ffn_drop=0.0),
+                    operation_order=["self_attn", "norm", "ffn", "norm"])),
+                positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True, offset=-0.5),
+                classes=["drivable_area", "ped_crossing", "walkway", "stop_line", "carpark_area", "divider"], loss="focal",
+                grid_transform=dict(input_scope=scopes[0], output_scope=scopes[1]))
+
+
+def test_bev_plugin_surface():
+    """BEV DDP fusion model + head: reference constructor arguments, state-dict keys and grid coordinates."""
+    from ddp_b200.bev import FUSIONMODELS, BevDDP, grid_coords
+    from oracle import bev_oracle as BO
+    for feat in (256, 512):
+        cfg = BO.BevConfig(feat_channels=feat)
+        kw = dict(type="DDP", bit_scale=0.01, timesteps=3, randsteps=5, time_difference=1, learned_sinusoidal_dim=16,
+                  sample_range=[0, 0.999], noise_schedule="cosine", diffusion="ddim",
+                  encoders=dict(camera=None, lidar=None), fuser=None, decoder=dict(backbone=None, neck=None),
+                  heads=dict(object=None, map=_bev_head_cfg((cfg.input_scope, cfg.output_scope))))
+        if feat != 512:
+            kw["feat_channels"] = feat
+        model = FUSIONMODELS.build(kw)
+        assert isinstance(model, BevDDP) and model.num_classes == 6 and model.threshold == 0.5
+        want = BO.make_weights(cfg, seed=0)
+        got = model.state_dict()
+        assert set(got) == set(want) and all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
+        gy, gx = model.heads["map"].grid_coords()
+        oy, ox = BO.grid_coords(cfg.input_scope, cfg.output_scope)
+        assert gy.numel() == 200 and torch.equal(gy, oy) and torch.equal(gx, ox)
+    with pytest.raises(ValueError, match="invalid noise schedule"):                  # fusion_models/ddp.py:102
+        FUSIONMODELS.build(dict(kw, noise_schedule="quadratic"))
+    with pytest.raises(NotImplementedError):
+        FUSIONMODELS.build(dict(kw, heads=dict(object=dict(type="TransFusionHead"), map=None)))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            model.ddim_sample([torch.zeros(1, 512, 128, 128)])
+    assert all(torch.equal(a, b) for a, b in zip(grid_coords(cfg.input_scope, cfg.output_scope), (oy, ox)))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_reference_bev_yaml_configs_build():
+    """The two shipped BEV DDP configs (model section + the head defaults of seg/default.yaml) build unchanged."""
+    import yaml
+    from ddp_b200.bev import FUSIONMODELS
+    base = yaml.safe_load(open(f"{REF}/bev/configs/nuscenes/default.yaml"))
+    seg = yaml.safe_load(open(f"{REF}/bev/configs/nuscenes/seg/default.yaml"))["model"]["heads"]["map"]
+    files = sorted(glob.glob(f"{REF}/bev/configs/nuscenes/seg/ddp-*.yaml"))
+    assert len(files) == 2
+    for f in files:
+        m = yaml.safe_load(open(f))["model"]
+        head = dict(seg, **m["heads"]["map"])           # recursive yaml inheritance of the BEV tree: child overrides parent
+        head["classes"] = base["map_classes"]          # ${map_classes}
+        m["heads"] = dict(object=None, map=head)
+        model = FUSIONMODELS.build(m)
+        assert model.timesteps == m["timesteps"] and model.randsteps == m["randsteps"] and model.bit_scale == 0.01
+        assert model.feat_channels == m.get("feat_channels", 512)
+        assert model.heads["map"].encoder.num_layers == 5
+
+
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 def test_reference_config_files_build_unchanged():
     files = sorted(glob.glob(f"{REF}/segmentation/configs/*/ddp_*.py"))

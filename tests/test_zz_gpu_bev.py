@@ -1,0 +1,110 @@
+"""GPU parity tests of the BEV map-segmentation variant through the C ABI: against the golden outputs
+of the unmodified reference BEV classes and against the oracle.
+
+STATUS: built after the round-1 GPU budget was spent.  What this variant adds around the (hardware-verified) denoiser is
+checked against the oracle by the host emulation (tests/test_bev_emu_cpu.py); the CUDA build of it has not run on
+hardware yet, hence `first_hw_run` (collected last, non-strict xfail — see tests/conftest.py).  Remove the marker after
+the first green GPU run.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import bev_oracle as BO
+from golden_util import golden_files, load_bev_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.first_hw_run(reason="BEV loop kernels: first hardware run pending (round-1 GPU budget spent)")]
+
+ATOL = 2e-4        # same fp32-summation-order tolerance as the segmentation path (values are probabilities here)
+
+
+def make_engine(cfg: BO.BevConfig, W, mode="tc_3xf16"):
+    from ddp_b200.bev import BevDecodeEngine
+    eng = BevDecodeEngine(timesteps=cfg.timesteps, time_difference=cfg.time_difference, bit_scale=cfg.bit_scale,
+                          threshold=cfg.threshold, feat_channels=cfg.feat_channels, num_layers=cfg.num_layers, gemm_mode=mode)
+    eng.load_state_dict(W)
+    return eng
+
+
+def check_maps(out, ref, what, thr=0.5):
+    """Probabilities agree to ATOL; thresholded maps agree except where the reference itself sits within ATOL of 0.5.
+    A flipped near-tie inside the loop perturbs its neighbourhood through the DDIM feedback: then require the bulk."""
+    d = (out - ref).abs()
+    flips = (out > thr) != (ref > thr)
+    if d.max().item() < ATOL:
+        assert int(flips.sum()) == 0 or float((ref[flips] - thr).abs().max()) < ATOL, what
+        return
+    frac = float((d > ATOL).float().mean())
+    print(f"[cascade] {what}: max|d| = {d.max().item():.2e}, {100 * frac:.3f}% of probabilities off by > {ATOL}")
+    assert frac < 0.02 and float(flips.float().mean()) < 2e-3, what
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc_3xf16"])
+@pytest.mark.parametrize("path", golden_files("bev"), ids=lambda p: os.path.basename(p)[:-4])
+def test_bev_matches_reference_golden(path, mode):
+    cfg, W, x, noise, g = load_bev_case(path)
+    gy, gx = BO.grid_coords(cfg.input_scope, cfg.output_scope)
+    out = make_engine(cfg, W, mode).sample(x.cuda(), noise[None].cuda(), gy, gx)
+    torch.cuda.synchronize()
+    check_maps(out.cpu(), torch.from_numpy(g["out"]), f"{os.path.basename(path)}[{mode}]")
+
+
+def test_bev_batched_equals_per_image_and_oracle():
+    cfg = BO.BevConfig(timesteps=2, randsteps=2, feat_channels=512, num_layers=5,
+                       input_scope=((-4.0, 4.0, 0.8), (-4.8, 4.8, 0.8)), output_scope=((-5.0, 5.0, 0.5), (-4.0, 6.0, 0.5)))
+    W = BO.make_weights(cfg, seed=3)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 512, 10, 12, generator=g)
+    noise = torch.randn(2, 2, 256, 10, 12, generator=g)
+    gy, gx = BO.grid_coords(cfg.input_scope, cfg.output_scope)
+    eng = make_engine(cfg, W)
+    out = eng.sample(x.cuda(), noise.cuda(), gy, gx)
+    check_maps(out.cpu(), BO.sample(W, cfg, x, noise), "bev 2 images, out-of-range grid")
+    for b in range(2):
+        one = eng.sample(x[b:b + 1].cuda(), noise[b:b + 1].cuda(), gy, gx)
+        assert torch.equal(one, out[b:b + 1])
+
+
+def test_bev_shipped_geometry_properties():
+    """128 x 128 state grid -> 200 x 200 map grid, T=3, R=5 (the shipped camera config): determinism and range."""
+    cfg = BO.BevConfig(feat_channels=256)
+    W = BO.make_weights(cfg, seed=7)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, 256, 128, 128, generator=g).cuda()
+    noise = torch.randn(1, 5, 256, 128, 128, generator=g).cuda()
+    gy, gx = BO.grid_coords(cfg.input_scope, cfg.output_scope)
+    eng = make_engine(cfg, W)
+    a = eng.sample(x, noise, gy, gx)
+    b = eng.sample(x, noise, gy, gx)
+    assert tuple(a.shape) == (1, 6, 200, 200) and torch.equal(a, b)
+    assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 and bool(torch.isfinite(a).all())
+
+
+def test_bev_plugin_ddim_sample():
+    from ddp_b200.bev import FUSIONMODELS
+    cfg = BO.BevConfig(timesteps=2, randsteps=2, feat_channels=256,
+                       input_scope=((-4.8, 4.8, 0.8), (-4.0, 4.0, 0.8)), output_scope=((-4.5, 4.5, 0.5), (-3.5, 3.5, 0.5)))
+    head = dict(type="DeformableHeadWithTime", in_channels=256, num_feature_levels=1,
+                encoder=dict(type="DetrTransformerEncoder", num_layers=5, transformerlayers=dict(
+                    type="BaseTransformerLayer", use_time_mlp=True,
+                    attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1, num_heads=8, dropout=0.0),
+                    ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                                  act_cfg=dict(type="GELU"), ffn_drop=0.0),
+                    operation_order=["self_attn", "norm", "ffn", "norm"])),
+                positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True, offset=-0.5),
+                classes=["drivable_area", "ped_crossing", "walkway", "stop_line", "carpark_area", "divider"], loss="focal",
+                grid_transform=dict(input_scope=cfg.input_scope, output_scope=cfg.output_scope))
+    model = FUSIONMODELS.build(dict(type="DDP", feat_channels=256, bit_scale=0.01, timesteps=2, randsteps=2,
+                                    heads=dict(object=None, map=head), encoders=None, fuser=None, decoder=None))
+    W = BO.make_weights(cfg, seed=11)
+    model.load_state_dict(W)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(1, 256, 12, 10, generator=g)
+    noise = torch.randn(1, 2, 256, 12, 10, generator=g)
+    out = model.ddim_sample([x.cuda()], model.heads["map"], noise=noise.cuda())
+    check_maps(out.cpu(), BO.ddim_sample_bev(W, cfg, x, noise[0]), "bev plug-in")
+    with pytest.raises(NotImplementedError):
+        model.ddpm_sample([x.cuda()])
