@@ -83,3 +83,42 @@ def make_inputs(task, randsteps, B, h, w, seed=1234):
     x = torch.randn(B, E, h, w, generator=g)
     noise = torch.randn(B, randsteps, cin, h, w, generator=g)
     return x, noise
+
+
+def make_neck_weights(in_channels, seed=0, out_channels=E) -> Dict[str, torch.Tensor]:
+    """FPN + MultiStageMerging weights under the reference's keys (``neck.0.*`` / ``neck.1.*``): xavier-uniform
+    convolutions as the reference's init_cfg asks (segmentation/mmseg/models/necks/fpn.py:82-83), GroupNorm affine
+    perturbed from (1, 0)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def xavier(*shape):
+        rf = shape[2] * shape[3]
+        a = math.sqrt(6.0 / (shape[1] * rf + shape[0] * rf))
+        return (torch.rand(*shape, generator=g) * 2 - 1) * a
+
+    W: Dict[str, torch.Tensor] = {}
+
+    def gn(prefix):
+        W[prefix + "gn.weight"] = 1.0 + 0.1 * torch.randn(out_channels, generator=g)
+        W[prefix + "gn.bias"] = 0.1 * torch.randn(out_channels, generator=g)
+
+    for i, c in enumerate(in_channels):
+        W[f"neck.0.lateral_convs.{i}.conv.weight"] = xavier(out_channels, c, 1, 1)
+        gn(f"neck.0.lateral_convs.{i}.")
+    for i in range(len(in_channels)):
+        W[f"neck.0.fpn_convs.{i}.conv.weight"] = xavier(out_channels, out_channels, 3, 3)
+        gn(f"neck.0.fpn_convs.{i}.")
+    W["neck.1.down.conv.weight"] = xavier(out_channels, out_channels * len(in_channels), 1, 1)
+    gn("neck.1.down.")
+    return W
+
+
+def make_bev_weights(feat_channels=512, num_layers=5, seed=0) -> Dict[str, torch.Tensor]:
+    """BEV map-segmentation weights (bev/mmdet3d/models/fusion_models/ddp.py:65-116): the segmentation recipe with 6
+    classes under the BEV tree's keys (``heads.map.*``) and a (256, feat_channels + 256) transform."""
+    W = make_weights(task="seg", num_classes=6, num_layers=num_layers, seed=seed)
+    if feat_channels != E:
+        g = torch.Generator().manual_seed(seed + 7919)
+        a = (6.0 / (feat_channels + 2 * E)) ** 0.5
+        W["transform.conv.weight"] = (torch.rand(E, feat_channels + E, 1, 1, generator=g) * 2 - 1) * a
+    return {("heads.map." + k[len("decode_head."):] if k.startswith("decode_head.") else k): v for k, v in W.items()}

@@ -122,6 +122,18 @@ def test_synthetic_recipe_equals_oracle_recipe():
         assert torch.equal(xa, xb) and torch.equal(na, nb)
 
 
+def test_synthetic_neck_and_bev_recipes_equal_oracle_recipes():
+    import torch
+    from ddp_b200 import synthetic as S
+    from oracle import bev_oracle as BO, neck_oracle as NO
+    a, b = NO.make_weights([96, 192, 384, 768], seed=5), S.make_neck_weights([96, 192, 384, 768], seed=5)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    for feat in (256, 512):
+        a = BO.make_weights(BO.BevConfig(feat_channels=feat), seed=6)
+        b = S.make_bev_weights(feat_channels=feat, num_layers=5, seed=6)
+        assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
 def test_ddpm_host_schedule_matches_oracle_formulas():
     import torch
     from ddp_b200 import schedule as S
