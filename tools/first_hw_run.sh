@@ -1,0 +1,30 @@
+#!/usr/bin/env bash
+# First hardware run of the rows built without a GPU (neck: DESIGN.md §9, BEV loop: §10).  Meant for ONE gpurun call:
+#
+#   gpurun --timeout 1500 -- 'bash tools/first_hw_run.sh'
+#
+# 1. the pending tests alone (short, so a fault is seen before anything long runs), under compute-sanitizer first;
+# 2. the whole GPU suite (verified tests first, the pending ones last: tests/conftest.py);
+# 3. device timing of both rows (tools/bench_rows.py) and an ncu launch list of each.
+# Everything lands in gpurun_out/first_hw_run/.  Every step has its own timeout; a failing step does not stop the next.
+set -u
+OUT=gpurun_out/first_hw_run
+mkdir -p "$OUT"
+run() { local name=$1; shift; echo "== $name: $*"; timeout "${T:-600}" "$@" > "$OUT/$name.log" 2>&1; echo "   exit $? (log: $OUT/$name.log)"; tail -n 5 "$OUT/$name.log"; }
+
+python __graft_entry__.py > "$OUT/build.log" 2>&1 || { echo "build failed"; tail -n 30 "$OUT/build.log"; exit 1; }
+T=900 run sanitizer_neck compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_neck.py -q -x --runxfail \
+    -k "swin_l or error_behaviour"
+T=900 run sanitizer_bev compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_bev.py -q -x --runxfail \
+    -k "fusion"
+T=600 run pending_neck python -m pytest tests/test_zz_gpu_neck.py -q --runxfail -rA
+T=600 run pending_bev python -m pytest tests/test_zz_gpu_bev.py -q --runxfail -rA
+T=1500 run gpu_suite python -m pytest tests -m gpu -q -rxX
+T=300 run bench_neck python tools/bench_rows.py neck
+T=300 run bench_bev python tools/bench_rows.py bev
+T=300 run bench_bev_fusion python tools/bench_rows.py bev --feat 512
+T=600 run ncu_neck ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$OUT/ncu_neck_launches.csv" \
+    python tools/bench_rows.py neck --steps 1
+T=600 run ncu_bev ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/ncu_bev_launches.csv" \
+    python tools/bench_rows.py bev --steps 1
+echo "done; see $OUT/"
