@@ -60,6 +60,10 @@ def _build_encoder_part(cfg):
         return fuse_neck([_build_encoder_part(c) for c in cfg])
     typ = cfg.get("type")
     if isinstance(typ, str) and typ not in MODELS:
+        from ..registry import host_framework_builder
+        host = host_framework_builder(typ)          # inside real mmseg / depth: the reference's own backbone / neck classes
+        if host is not None:
+            return host.build(cfg)
         warnings.warn(f"'{typ}' is not registered; using a placeholder (the encoder is outside the ddp_b200 hot path)")
         return _MissingEncoder(**cfg)
     return MODELS.build(cfg)

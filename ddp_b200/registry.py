@@ -77,23 +77,56 @@ def build_depther(cfg, train_cfg=None, test_cfg=None):
     return DEPTHER.build(cfg, train_cfg=train_cfg, test_cfg=test_cfg)
 
 
-def register_into_mmseg():
-    """Register the B200 classes into the real mmseg / depth registries (force=True).  Returns what was done."""
+def host_framework_builder(typ):
+    """A class named `typ` from the host framework's own registries (real mmseg / depth toolbox), or None.
+    Used for the parts of a config that are outside ddp_b200's scope (backbones, stock necks) when the plug-ins run
+    inside the reference: the reference's registries build them, exactly as they would without ddp_b200."""
+    for mod in ("mmseg.models.builder", "depth.models.builder"):
+        try:
+            m = __import__(mod, fromlist=["BACKBONES", "NECKS"])
+        except ImportError:
+            continue
+        for reg in (getattr(m, "BACKBONES", None), getattr(m, "NECKS", None)):
+            if reg is not None and reg.get(typ) is not None:
+                return reg
+    return None
+
+
+def register_into_mmseg(necks=False):
+    """Register the B200 classes into the real mmseg / depth / mmdet3d registries (force=True).  Returns what was done.
+
+    The DDP segmentors build ``neck=[FPN, MultiStageMerging]`` into the fused CUDA neck by themselves; ``necks=True``
+    additionally REPLACES the stock ``FPN`` / ``MultiStageMerging`` entries of the host registries (only do that in a
+    process that runs nothing but DDP configs: the replacements refuse arguments those configs do not use)."""
     done = []
     from .models import ddp as seg_mod, depth_ddp as depth_mod, deformable_head_with_time as head_mod
+    from . import neck as neck_mod, bev as bev_mod
     try:
-        from mmseg.models.builder import SEGMENTORS as S, HEADS as H
+        from mmseg.models.builder import SEGMENTORS as S, HEADS as H, NECKS as N
         S.register_module(name="DDP", force=True, module=seg_mod.DDP)
         S.register_module(name="SelfAlignedDDP", force=True, module=seg_mod.SelfAlignedDDP)
         H.register_module(name="DeformableHeadWithTime", force=True, module=head_mod.DeformableHeadWithTime)
+        if necks:
+            N.register_module(name="FPN", force=True, module=neck_mod.FPN)
+            N.register_module(name="MultiStageMerging", force=True, module=neck_mod.MultiStageMerging)
         done.append("mmseg")
     except ImportError:
         pass
     try:
-        from depth.models.builder import DEPTHER as D, HEADS as DH
+        from depth.models.builder import DEPTHER as D, HEADS as DH, NECKS as DN
         D.register_module(name="DDP", force=True, module=depth_mod.DDP)
         DH.register_module(name="DeformableHeadWithTime", force=True, module=head_mod.DepthDeformableHeadWithTime)
+        if necks:
+            DN.register_module(name="FPN", force=True, module=neck_mod.FPN)
+            DN.register_module(name="MultiStageMerging", force=True, module=neck_mod.MultiStageMerging)
         done.append("depth")
+    except ImportError:
+        pass
+    try:        # bev/mmdet3d/models/builder.py: FUSIONMODELS / HEADS
+        from mmdet3d.models.builder import FUSIONMODELS as F3, HEADS as H3
+        F3.register_module(name="DDP", force=True, module=bev_mod.BevDDP)
+        H3.register_module(name="DeformableHeadWithTime", force=True, module=bev_mod.BevDeformableHeadWithTime)
+        done.append("mmdet3d")
     except ImportError:
         pass
     return done

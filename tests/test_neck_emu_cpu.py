@@ -9,7 +9,6 @@ import ctypes
 import os
 import subprocess
 
-import numpy as np
 import pytest
 import torch
 

@@ -202,6 +202,18 @@ def test_reference_config_files_build_unchanged():
             assert isinstance(model.neck, FusedNeck)
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_drop_in_inside_the_reference_tree():
+    """INTEGRATION.md scenario A on the host side, inside the reference's own mmseg (subprocess: the import shim
+    rewires `mmcv`): register_into_mmseg() -> the reference's build_segmentor builds the unchanged config into
+    ddp_b200.DDP with the reference's own Swin backbone and the fused CUDA neck; a reference state dict loads by key."""
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(HERE, "fixtures", "inside_reference.py")], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "INSIDE-REFERENCE-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_shard_bounds_cover_batch():
     for B in (1, 5, 8, 64):
         for W in (1, 2, 3, 8):
