@@ -360,7 +360,7 @@ def main():
         del eng3
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:        # the CPU leg is reported on rank 0 at N = 1 only
         cfg = oracle_cfg(wl)
         cores, thread_log = pick_cpu_threads(cfg, W, x[:1], noise[:1])
         nsteps = 2 if wl["h"] * wl["w"] >= 16384 else min(wl["T"], 4)
