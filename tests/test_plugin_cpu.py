@@ -212,6 +212,10 @@ def test_drop_in_inside_the_reference_tree():
     res = subprocess.run([sys.executable, os.path.join(HERE, "fixtures", "inside_reference.py")], capture_output=True,
                          text=True, timeout=600)
     assert res.returncode == 0 and "INSIDE-REFERENCE-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    # the depth toolbox: reference build_depther + unchanged NYU config + the reference's own Swin backbone
+    res = subprocess.run([sys.executable, os.path.join(HERE, "fixtures", "inside_reference_depth.py")], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "INSIDE-REFERENCE-DEPTH-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
 def test_shard_bounds_cover_batch():
