@@ -122,10 +122,14 @@ class BevDecodeEngine:
             self._check(self.lib.ddp_bev_plan(self._h, B, R, h, w, gy.numel(), gx.numel(),
                                               ctypes.cast(gy.data_ptr(), fp), ctypes.cast(gx.data_ptr(), fp),
                                               ctypes.byref(nbytes)))
-        if self._ws is None or self._ws.numel() < nbytes.value:
-            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        if self._ws is None or self._ws.numel() < nbytes.value + 256:
+            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+        self._ws_bytes = nbytes.value
         self._plan = key
         self._out_hw = (gy.numel(), gx.numel())
+
+    def _ws_ptr(self):
+        return (self._ws.data_ptr() + 255) // 256 * 256          # the library wants a 256-byte aligned workspace
 
     @property
     def last_launch_count(self):
@@ -151,7 +155,7 @@ class BevDecodeEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self._check(self.lib.ddp_bev_sample(self._h, vp(x.data_ptr()), vp(noise.data_ptr()), vp(out.data_ptr()),
-                                                vp(self._ws.data_ptr()), self._ws.numel(), vp(stream)))
+                                                vp(self._ws_ptr()), self._ws_bytes, vp(stream)))
         return out
 
 

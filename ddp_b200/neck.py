@@ -95,9 +95,13 @@ class NeckEngine:
         ws = (ctypes.c_int32 * self.levels)(*[s[1] for s in sizes])
         nbytes = ctypes.c_size_t()
         self._check(self.lib.ddp_neck_plan(self._h, B, hs, ws, ctypes.byref(nbytes)))
-        if self._ws is None or self._ws.numel() < nbytes.value:
-            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        if self._ws is None or self._ws.numel() < nbytes.value + 256:
+            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+        self._ws_bytes = nbytes.value
         self._plan = key
+
+    def _ws_ptr(self):
+        return (self._ws.data_ptr() + 255) // 256 * 256          # the library wants a 256-byte aligned workspace
 
     @property
     def last_launch_count(self):
@@ -131,7 +135,7 @@ class NeckEngine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             self._check(self.lib.ddp_neck_forward(self._h, in_ptrs, vp(x_out.data_ptr()) if merge else None, fpn_ptrs,
-                                                  vp(self._ws.data_ptr()), self._ws.numel(), vp(stream)))
+                                                  vp(self._ws_ptr()), self._ws_bytes, vp(stream)))
         return x_out, fpn
 
 
