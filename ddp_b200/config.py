@@ -1,8 +1,11 @@
 """Loader for the reference's mmcv-style python config files (``_base_`` inheritance, ``_delete_`` keys,
 attribute access), so that ``segmentation/configs/{ade,cityscapes}/ddp_*.py`` and
-``depth/configs/ddp_*/*.py`` load unchanged without mmcv (reference: mmcv.utils.config.Config)."""
+``depth/configs/ddp_*/*.py`` load unchanged without mmcv (reference: mmcv.utils.config.Config), and for the BEV
+tree's yaml configs (``bev/configs/nuscenes/seg/ddp-*.yaml``: torchpack's ``configs.load(path, recursive=True)`` —
+every ``default.yaml`` from the configs root down to the file's directory, then the file, ``${expr}`` interpolation)."""
 import copy
 import os
+import re
 
 BASE_KEY = "_base_"
 DELETE_KEY = "_delete_"
@@ -76,3 +79,57 @@ class Config(ConfigDict):
             cfg[k] = v
         cfg.__dict__["filename"] = path
         return cfg
+
+
+# ---- torchpack-style yaml configs of the BEV tree -------------------------------------------------------------------
+def _merge_yaml(a, b):
+    out = dict(a)
+    for k, v in b.items():
+        out[k] = _merge_yaml(out[k], v) if isinstance(v, dict) and isinstance(out.get(k), dict) else copy.deepcopy(v)
+    return out
+
+
+_INTERP = re.compile(r"^\$\{(.*)\}$", re.S)
+
+
+def _resolve(node, root):
+    """Evaluate ``${expr}`` strings against the whole config (attribute access, e.g. ``${augment2d.resize[0]}``)."""
+    if isinstance(node, dict):
+        return {k: _resolve(v, root) for k, v in node.items()}
+    if isinstance(node, list):
+        return [_resolve(v, root) for v in node]
+    if isinstance(node, str):
+        m = _INTERP.match(node.strip())
+        if m:
+            return eval(m.group(1), {"__builtins__": {}}, _wrap(root))      # noqa: S307 - config expressions, as torchpack does
+    return node
+
+
+def load_yaml(path, recursive=True):
+    """The reference BEV tree's ``configs.load(path, recursive=True)``: defaults of every directory level, then the file."""
+    import yaml
+    path = os.path.abspath(path)
+    chain = [path]
+    if recursive:
+        d = os.path.dirname(path)
+        while True:
+            f = os.path.join(d, "default.yaml")
+            if os.path.exists(f) and f != path:
+                chain.append(f)
+            if os.path.basename(d) == "configs" or os.path.dirname(d) == d:
+                break
+            d = os.path.dirname(d)
+    cfg = {}
+    for f in reversed(chain):
+        with open(f) as fh:
+            cfg = _merge_yaml(cfg, yaml.safe_load(fh) or {})
+    for _ in range(8):                     # references to values that are themselves interpolated
+        new = _resolve(cfg, cfg)
+        if new == cfg:
+            break
+        cfg = new
+    out = Config()
+    for k, v in cfg.items():
+        out[k] = v
+    out.__dict__["filename"] = path
+    return out

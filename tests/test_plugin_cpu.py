@@ -159,22 +159,23 @@ def test_bev_plugin_surface():
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
 def test_reference_bev_yaml_configs_build():
-    """The two shipped BEV DDP configs (model section + the head defaults of seg/default.yaml) build unchanged."""
-    import yaml
+    """The two shipped BEV DDP configs load UNCHANGED (torchpack-style recursive defaults + ${...} interpolation) and build."""
     from ddp_b200.bev import FUSIONMODELS
-    base = yaml.safe_load(open(f"{REF}/bev/configs/nuscenes/default.yaml"))
-    seg = yaml.safe_load(open(f"{REF}/bev/configs/nuscenes/seg/default.yaml"))["model"]["heads"]["map"]
+    from ddp_b200.config import load_yaml
     files = sorted(glob.glob(f"{REF}/bev/configs/nuscenes/seg/ddp-*.yaml"))
     assert len(files) == 2
     for f in files:
-        m = yaml.safe_load(open(f))["model"]
-        head = dict(seg, **m["heads"]["map"])           # recursive yaml inheritance of the BEV tree: child overrides parent
-        head["classes"] = base["map_classes"]          # ${map_classes}
-        m["heads"] = dict(object=None, map=head)
+        cfg = load_yaml(f)
+        m = cfg.model
+        assert m.type == "DDP" and cfg.max_epochs == cfg.runner.max_epochs            # child overrides parent; ${max_epochs}
+        assert m.heads.map.classes == cfg.map_classes and len(cfg.map_classes) == 6    # ${map_classes}
+        assert m.heads.map.grid_transform.output_scope == [[-50, 50, 0.5], [-50, 50, 0.5]]      # from seg/default.yaml
+        assert m.encoders.camera.vtransform.feature_size == [256 // 8, 704 // 8]      # ${[image_size[0] // 8, image_size[1] // 8]}
         model = FUSIONMODELS.build(m)
-        assert model.timesteps == m["timesteps"] and model.randsteps == m["randsteps"] and model.bit_scale == 0.01
+        assert model.timesteps == m.timesteps and model.randsteps == m.randsteps and model.bit_scale == 0.01
         assert model.feat_channels == m.get("feat_channels", 512)
         assert model.heads["map"].encoder.num_layers == 5
+        assert model.heads["map"].grid_coords()[0].numel() == 200
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
