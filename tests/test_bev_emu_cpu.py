@@ -4,7 +4,7 @@ ddp_b200/csrc/bev_plan.h holds what the BEV variant adds around the (shared, har
 feat_channels-wide transform, the grid_sample onto the output grid, sigmoid accumulation, threshold -> nearest resize ->
 mean class embedding -> DDIM update.  tests/emu/bev_emu.cpp runs exactly that code on the CPU with the denoiser
 replaced by a replay of the oracle's per-step logits (teacher forcing).  A CHECK of the product's indexing and
-arithmetic, not a product path.  The CUDA build is covered by tests/test_zz_gpu_bev.py.
+arithmetic, not a product path.  The CUDA build is covered by tests/test_zzz_gpu_bev.py.
 """
 import ctypes
 import os

@@ -15,10 +15,10 @@ run() { local name=$1; shift; echo "== $name: $*"; timeout "${T:-600}" "$@" > "$
 python __graft_entry__.py > "$OUT/build.log" 2>&1 || { echo "build failed"; tail -n 30 "$OUT/build.log"; exit 1; }
 T=900 run sanitizer_neck compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_neck.py -q -x --runxfail \
     -k "swin_l or error_behaviour"
-T=900 run sanitizer_bev compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_gpu_bev.py -q -x --runxfail \
+T=900 run sanitizer_bev compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zzz_gpu_bev.py -q -x --runxfail \
     -k "fusion"
 T=600 run pending_neck python -m pytest tests/test_zz_gpu_neck.py -q --runxfail -rA
-T=600 run pending_bev python -m pytest tests/test_zz_gpu_bev.py -q --runxfail -rA
+T=600 run pending_bev python -m pytest tests/test_zzz_gpu_bev.py -q --runxfail -rA
 T=1500 run gpu_suite python -m pytest tests -m gpu -q -rxX
 T=300 run bench_neck python tools/bench_rows.py neck
 T=300 run bench_bev python tools/bench_rows.py bev
