@@ -6,6 +6,10 @@
 //
 // Included at the end of ddp_b200.cu (same translation unit: it reaches into ddp_handle).
 #pragma once
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
 #include <string>
 #include <vector>
 

@@ -7,6 +7,10 @@
 //
 // Included at the end of ddp_b200.cu (one translation unit: the kernels of kernels.cuh are not inline).
 #pragma once
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
 #include <string>
 #include <vector>
 
