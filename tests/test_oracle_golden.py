@@ -61,6 +61,27 @@ def test_schedule_known_answers():
     assert d20[0] == (1.0, pytest.approx(0.9)) and d20[1] == (pytest.approx(0.95), pytest.approx(0.85))
 
 
+def test_linear_schedule_known_answers():
+    """noise_schedule='linear' (ddp.py:18-19, no shipped config uses it): values of the reference's own
+    beta_linear_log_snr / log_snr_to_alpha_sigma, evaluated here through the import shim when this test was written."""
+    t = torch.tensor([1.0, 2 / 3, 1 / 3, 0.0, 0.5, 0.9])
+    want_l = torch.tensor([-10.000054359436035, -4.432733058929443, -0.7119865417480469, 9.21028995513916,
+                           -2.4144582748413086, -8.099796295166016])
+    want_a = torch.tensor([0.006737610790878534, 0.108362577855587, 0.5737246870994568, 0.9999499917030334,
+                           0.2864904999732971, 0.017421504482626915])
+    want_s = torch.tensor([0.9999772906303406, 0.9941114783287048, 0.8190482258796692, 0.009999752044677734,
+                           0.9580830335617065, 0.9998482465744019])
+    l = O.log_snr_linear(t)
+    a, s = O.alpha_sigma(l)
+    assert torch.allclose(l, want_l, rtol=2e-6, atol=0) and torch.allclose(a, want_a, rtol=2e-6, atol=0)
+    assert torch.allclose(s, want_s, rtol=2e-6, atol=0)
+    # the host schedule handed to the library takes the same branch
+    from ddp_b200 import schedule as S
+    ls, a3, s3, an3, sn3 = S.seg_schedule(3, 1, (0, 0.999), "linear")
+    assert ls[0] == pytest.approx(float(want_l[0]), rel=2e-6) and a3[1] == pytest.approx(float(want_a[1]), rel=2e-6)
+    assert an3[0] == pytest.approx(float(want_a[2]), rel=2e-6) and sn3[2] == pytest.approx(float(want_s[3]), rel=2e-6)
+
+
 def test_batched_equals_per_image_loop():
     cfg = O.OracleConfig(task="seg", num_classes=7, timesteps=2, randsteps=2)
     W = O.make_weights(cfg, seed=3)
