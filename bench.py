@@ -178,6 +178,8 @@ def run_reference(args, wl, name):
         return
     W, x, noise = make_weights_and_inputs(wl, 1, seed=1234)
     cfg = oracle_cfg(wl)
+    if args.reference_device == "cuda":
+        return run_reference_on_gpu(args, wl, name, cfg, W, x, noise)
     cores, thread_log = pick_cpu_threads(cfg, W, x, noise)
     for _ in range(args.warmup):
         cpu_reference_step(cfg, W, x, noise, 1)
@@ -192,6 +194,38 @@ def run_reference(args, wl, name):
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"1 image x 1 of {wl['T']} DDIM steps per bench step, images/s = 1/(T*t_step); "
                                    f"torch threads chosen by timing one step each: {thread_log} s of {os.cpu_count()} cores"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_reference_on_gpu(args, wl, name, cfg, W, x, noise):
+    """--impl reference --reference-device cuda (opt-in, SURVEY 8d "oracle-on-GPU"): the reference's own PyTorch op
+    sequence (the oracle port) executed eagerly on cuda:0 — what the reference does on a GPU box except that its
+    deformable attention goes through the grid_sample branch of mmcv's Python fallback instead of mmcv-full's CUDA op
+    (not installable here).  One image per step (the reference loop is defined for b = 1), all T DDIM steps."""
+    from oracle import ddp_oracle as O
+    dev = torch.device("cuda", 0)
+    Wd = {k: v.to(dev) for k, v in W.items()}
+    xd, nd = x.to(dev), noise.to(dev)
+    for _ in range(max(args.warmup, 1)):
+        O.sample(Wd, cfg, xd, nd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        O.sample(Wd, cfg, xd, nd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    value = 1.0 / (ms / 1e3)
+    line = {
+        "impl": "reference", "reference_device": "cuda", "metric": "images/sec", "value": value, "unit": "images/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, name, 1, args),
+        "note": "oracle-on-GPU: the reference's PyTorch op sequence run eagerly on the same B200, 1 image per call, all "
+                f"{wl['T']} DDIM steps; deformable attention through grid_sample (mmcv's Python fallback), not mmcv-full's CUDA op",
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -216,6 +250,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm", default=os.environ.get("DDP_GEMM", "tc_3xf16"), choices=["fp32", "tc_3xf16", "tc_f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
+                    help="with --impl reference: cpu (default, the measurement contract) or cuda (oracle-on-GPU comparison)")
     ap.add_argument("--per-gpu", type=int, default=0, help="override images per GPU")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])

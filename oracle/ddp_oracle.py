@@ -204,15 +204,16 @@ def time_mlp(W, l):
 # head
 # --------------------------------------------------------------------------
 def sine_pe(rows, h, w, dtype, num_feats=128, temperature=10000, scale=2 * math.pi,
-            eps=1e-6, offset=-0.5):
-    """(rows, 256, h, w); normalize=True as in every DDP config."""
-    mask = torch.zeros((rows, h, w)).to(torch.int)
+            eps=1e-6, offset=-0.5, device=None):
+    """(rows, 256, h, w); normalize=True as in every DDP config.  Built on `device` like the reference (the mask is
+    allocated on feat.device, deformable_head_with_time.py:102)."""
+    mask = torch.zeros((rows, h, w), device=device).to(torch.int)
     not_mask = 1 - mask
     y_embed = not_mask.cumsum(1, dtype=torch.float32)
     x_embed = not_mask.cumsum(2, dtype=torch.float32)
     y_embed = (y_embed + offset) / (y_embed[:, -1:, :] + eps) * scale
     x_embed = (x_embed + offset) / (x_embed[:, :, -1:] + eps) * scale
-    dim_t = torch.arange(num_feats, dtype=torch.float32)
+    dim_t = torch.arange(num_feats, dtype=torch.float32, device=device)
     dim_t = temperature ** (2 * (dim_t // 2) / num_feats)
     pos_x = x_embed[:, :, :, None] / dim_t
     pos_y = y_embed[:, :, :, None] / dim_t
@@ -223,10 +224,10 @@ def sine_pe(rows, h, w, dtype, num_feats=128, temperature=10000, scale=2 * math.
     return pos.to(dtype)
 
 
-def reference_points(h, w, dtype):
+def reference_points(h, w, dtype, device=None):
     ref_y, ref_x = torch.meshgrid(
-        torch.linspace(0.5, h - 0.5, h, dtype=torch.float32),
-        torch.linspace(0.5, w - 0.5, w, dtype=torch.float32), indexing="ij")
+        torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device),
+        torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device), indexing="ij")
     ref_y = ref_y.reshape(-1)[None] / h
     ref_x = ref_x.reshape(-1)[None] / w
     ref = torch.stack((ref_x, ref_y), -1)
@@ -264,7 +265,7 @@ def msda(W, p, query, query_pos, ref, h, w, taps=None):
     aw = F.linear(query, W[p + "attention_weights.weight"], W[p + "attention_weights.bias"]) \
         .view(bs, nq, HEADS, POINTS)
     aw = aw.softmax(-1).view(bs, nq, HEADS, 1, POINTS)
-    normalizer = torch.tensor([[w, h]], dtype=torch.long)
+    normalizer = torch.tensor([[w, h]], dtype=torch.long, device=query.device)
     loc = ref[:, :, None, :, None, :] + off / normalizer[None, None, None, :, None, :]
     out = msda_gather(value, h, w, loc, aw)
     if taps is not None:
@@ -299,9 +300,9 @@ def encoder_layer(W, j, query, query_pos, ref, h, w, time, taps=None):
 def head_tokens(W, cfg: OracleConfig, feat, time, taps: Optional[list] = None):
     """feat (rows, 256, h, w); time (1 or rows, 1024) -> memory (rows, 256, h, w)."""
     rows, c, h, w = feat.shape
-    pos = sine_pe(rows, h, w, feat.dtype).flatten(2).transpose(1, 2)
+    pos = sine_pe(rows, h, w, feat.dtype, device=feat.device).flatten(2).transpose(1, 2)
     q = feat.flatten(2).transpose(1, 2)
-    ref = reference_points(h, w, feat.dtype)
+    ref = reference_points(h, w, feat.dtype, device=feat.device)
     q = q.permute(1, 0, 2)
     pos = pos.permute(1, 0, 2)
     for j in range(cfg.num_layers):
@@ -357,7 +358,7 @@ def _sample_seg_one(W, cfg: OracleConfig, x, noise, trace: Optional[Trace], ddpm
     outs = []
     mask_logit = None
     for idx, (t_now, t_next) in enumerate(time_pairs_seg(cfg)):
-        times = torch.tensor([t_now, t_next])          # float32, as in the reference
+        times = torch.tensor([t_now, t_next], device=x.device)          # float32, as in the reference
         times_now = times[0:1].to(dtype)
         times_next = times[1:2].to(dtype)
         feat = torch.cat([xr, mask_t], dim=1)
@@ -419,7 +420,7 @@ def _sample_depth_one(W, cfg: OracleConfig, x, noise, trace: Optional[Trace]):
     depth_t = noise
     depth_pred = None
     for (t_now, t_next) in time_pairs_depth(cfg):
-        times = torch.tensor([t_now, t_next])
+        times = torch.tensor([t_now, t_next], device=x.device)
         times_now = times[0:1].to(dtype)
         times_next = times[1:2].to(dtype)
         feat = torch.cat([xr, depth_t], dim=1)

@@ -27,4 +27,7 @@ T=600 run ncu_neck ncu --metrics gpu__time_duration.sum --clock-control none -c 
     python tools/bench_rows.py neck --steps 1
 T=600 run ncu_bev ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/ncu_bev_launches.csv" \
     python tools/bench_rows.py bev --steps 1
+# the north star's comparator: the reference's PyTorch op sequence on the SAME B200 (opt-in arm)
+T=600 run oracle_on_gpu_T10 python bench.py --impl reference --reference-device cuda --steps 3 --warmup 1
+T=600 run oracle_on_gpu_T3 python bench.py --impl reference --reference-device cuda --steps 3 --warmup 1 --workload cityscapes_512x1024_T3
 echo "done; see $OUT/"
