@@ -22,6 +22,20 @@ def test_header_declares_expected_entry_points():
         assert s in syms
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/ddp_b200.h must compile as C99 (what a cgo / FFI binding would include)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ddp_b200.h"\nint main(void) { ddp_config c; ddp_neck_config n; ddp_bev_config b; '
+                   '(void)c; (void)n; (void)b; return DDP_ABI_VERSION - 1; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I",
+                          os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_library_exports_every_declared_symbol():
     from ddp_b200 import build, _lib
     build.build()
