@@ -27,6 +27,13 @@ T=600 run ncu_neck ncu --metrics gpu__time_duration.sum --clock-control none -c 
     python tools/bench_rows.py neck --steps 1
 T=600 run ncu_bev ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/ncu_bev_launches.csv" \
     python tools/bench_rows.py bev --steps 1
+# micro-benchmarks behind the round-2 kernel plan (profiles/r02_plan.md): built here if the binaries did not travel
+for u in ubench_gather ubench_sw_a; do
+    [ -x tools/$u ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/$u tools/$u.cu -lcuda > "$OUT/build_$u.log" 2>&1
+done
+T=300 run ubench_gather_s05 tools/ubench_gather 0.5
+T=300 run ubench_gather_s20 tools/ubench_gather 2.0
+T=120 run ubench_sw_a tools/ubench_sw_a
 # the north star's comparator: the reference's PyTorch op sequence on the SAME B200 (opt-in arm)
 T=600 run oracle_on_gpu_T10 python bench.py --impl reference --reference-device cuda --steps 3 --warmup 1
 T=600 run oracle_on_gpu_T3 python bench.py --impl reference --reference-device cuda --steps 3 --warmup 1 --workload cityscapes_512x1024_T3

@@ -1,0 +1,216 @@
+// Micro-benchmark for the deformable gather (k_msda_gather, 20 % of the decode step): is it bound by how its tokens are
+// ORDERED over the SMs?  ncu of round 1: L1 wavefronts 60 %, L1 hit rate 57 % — the 43 % of 16 KB per token that miss L1
+// come from L2 at ~6 TB/s, so locality in L1 may be the lever.  Variants, all with the kernel's exact arithmetic
+// (outputs are compared bit for bit with the product kernel):
+//   v0  the product kernel: warp = token in row-major order, 8 consecutive tokens per CTA, CTAs scheduled by the hardware
+//   v1  persistent CTAs (k per SM), each walking a CONTIGUOUS range of 8 x 8 token tiles in row-major tile order
+//   v2  as v1 with the tiles in Morton (Z) order, so that consecutive tiles of a CTA are 2-D neighbours
+//   v3  as v2, head group 0 for the whole tile, then head group 1 (halves the L1 working set of a tile)
+// Geometry = the headline shape (8 rows x 128 x 256 tokens); sampling records synthesised like the synthetic weights
+// produce them: the reference's ring bias (direction = head, radius = point + 1) plus N(0, sigma) pixels.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/ubench_gather tools/ubench_gather.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../ddp_b200/csrc/common.cuh"
+#include "../ddp_b200/csrc/kernels.cuh"
+using namespace ddp;
+
+// one head group (4 heads) of one token: the body of k_msda_gather, verbatim arithmetic
+__device__ __forceinline__ void gather_group(const float* __restrict__ V, const uint32_t* __restrict__ rec, __half* out_hi,
+                                             __half* out_lo, int N, int W, int token, int hg, int lane) {
+    const int row = token / N;
+    const uint32_t* rp = rec + (size_t)token * kRecW;
+    const int m = hg * 4 + (lane >> 3);
+    const int ch = m * kHeadDim + (lane & 7) * 4;
+    const float* Vr = V + (size_t)row * N * kE + ch;
+    const uint4 wd = *reinterpret_cast<const uint4*>(rp + m * 4);
+    const float4 fx = *reinterpret_cast<const float4*>(rp + 32 + m * 4);
+    const float4 fy = *reinterpret_cast<const float4*>(rp + 64 + m * 4);
+    const float4 aw = *reinterpret_cast<const float4*>(rp + 96 + m * 4);
+    const uint32_t w4[4] = {wd.x, wd.y, wd.z, wd.w};
+    const float fx4[4] = {fx.x, fx.y, fx.z, fx.w}, fy4[4] = {fy.x, fy.y, fy.z, fy.w}, a4[4] = {aw.x, aw.y, aw.z, aw.w};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 vv[kPoints][4];
+#pragma unroll
+    for (int p = 0; p < kPoints; ++p) {
+        const uint32_t wv = w4[p];
+        const int base = (int)(wv & 0x03FFFFFFu);
+        const int dx = (int)((wv >> 26) & 1u);
+        const int dy = ((wv >> 27) & 1u) ? W : 0;
+        vv[p][0] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)base * kE));
+        vv[p][1] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dx) * kE));
+        vv[p][2] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy) * kE));
+        vv[p][3] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy + dx) * kE));
+    }
+#pragma unroll
+    for (int p = 0; p < kPoints; ++p) {
+        const uint32_t wv = w4[p];
+        const float wx1 = fx4[p], wy1 = fy4[p], wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+        const float c00 = (wv & (1u << 28)) ? wy0 * wx0 : 0.f;
+        const float c01 = (wv & (1u << 29)) ? wy0 * wx1 : 0.f;
+        const float c10 = (wv & (1u << 30)) ? wy1 * wx0 : 0.f;
+        const float c11 = (wv & (1u << 31)) ? wy1 * wx1 : 0.f;
+        const float4 v00 = vv[p][0], v01 = vv[p][1], v10 = vv[p][2], v11 = vv[p][3];
+        float s0 = c00 * v00.x, s1 = c00 * v00.y, s2 = c00 * v00.z, s3 = c00 * v00.w;
+        s0 = fmaf(c01, v01.x, s0); s1 = fmaf(c01, v01.y, s1); s2 = fmaf(c01, v01.z, s2); s3 = fmaf(c01, v01.w, s3);
+        s0 = fmaf(c10, v10.x, s0); s1 = fmaf(c10, v10.y, s1); s2 = fmaf(c10, v10.z, s2); s3 = fmaf(c10, v10.w, s3);
+        s0 = fmaf(c11, v11.x, s0); s1 = fmaf(c11, v11.y, s1); s2 = fmaf(c11, v11.z, s2); s3 = fmaf(c11, v11.w, s3);
+        acc[0] = fmaf(a4[p], s0, acc[0]); acc[1] = fmaf(a4[p], s1, acc[1]);
+        acc[2] = fmaf(a4[p], s2, acc[2]); acc[3] = fmaf(a4[p], s3, acc[3]);
+    }
+    const size_t o = (size_t)token * kE + ch;
+    const float a0 = acc[0] * kSplitScale, a1 = acc[1] * kSplitScale, a2 = acc[2] * kSplitScale, a3 = acc[3] * kSplitScale;
+    __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+    *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+    const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+    __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y), l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+    *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+}
+
+__host__ __device__ inline uint32_t morton_decode_x(uint32_t z) {          // even bits
+    z &= 0x55555555u; z = (z | (z >> 1)) & 0x33333333u; z = (z | (z >> 2)) & 0x0F0F0F0Fu;
+    z = (z | (z >> 4)) & 0x00FF00FFu; z = (z | (z >> 8)) & 0x0000FFFFu;
+    return z;
+}
+
+// tile t (8 x 8 tokens) of image `row` -> its top-left token; tiles_x x tiles_y tiles per image (powers of two for Z order)
+template <bool ZORDER>
+__host__ __device__ inline void tile_origin(int t, int tiles_x, int tiles_y, int& row, int& ti, int& tj) {
+    const int per_img = tiles_x * tiles_y;
+    row = t / per_img;
+    const int r = t - row * per_img;
+    if (ZORDER) {
+        // tiles_x = 2 tiles_y here (32 x 16): Z-order inside each 16 x 16 half, halves side by side
+        const int half = r / (tiles_y * tiles_y), z = r - half * tiles_y * tiles_y;
+        tj = (int)morton_decode_x((uint32_t)z) + half * tiles_y;
+        ti = (int)morton_decode_x((uint32_t)z >> 1);
+    } else {
+        ti = r / tiles_x;
+        tj = r - ti * tiles_x;
+    }
+}
+
+// persistent CTAs: CTA c walks tiles [c * n / G, (c + 1) * n / G); 8 warps, warp w takes tile rows w (8 tokens each)
+template <bool ZORDER, bool GROUP_MAJOR>
+__global__ void __launch_bounds__(256, 4)
+k_gather_tiled(const float* __restrict__ V, const uint32_t* __restrict__ rec, __half* out_hi, __half* out_lo, int H, int W,
+               int n_tiles) {
+    const int N = H * W, tiles_x = W / 8, tiles_y = H / 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = (long long)blockIdx.x * n_tiles / gridDim.x, t1 = (long long)(blockIdx.x + 1) * n_tiles / gridDim.x;
+    for (int t = (int)t0; t < (int)t1; ++t) {
+        int row, ti, tj;
+        tile_origin<ZORDER>(t, tiles_x, tiles_y, row, ti, tj);
+        const int tok0 = row * N + (ti * 8 + warp) * W + tj * 8;
+        if (GROUP_MAJOR) {
+            for (int hg = 0; hg < 2; ++hg) {
+                for (int x = 0; x < 8; ++x) gather_group(V, rec, out_hi, out_lo, N, W, tok0 + x, hg, lane);
+                __syncthreads();           // the whole tile finishes a head group before the next one starts
+            }
+        } else {
+            for (int x = 0; x < 8; ++x) {
+                gather_group(V, rec, out_hi, out_lo, N, W, tok0 + x, 0, lane);
+                gather_group(V, rec, out_hi, out_lo, N, W, tok0 + x, 1, lane);
+            }
+        }
+    }
+}
+
+// sampling records as the sampling projection's epilogue writes them, from synthetic offsets
+__global__ void k_make_records(uint32_t* rec, int H, int W, int total, float sigma, uint32_t seed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head * 4 + point)
+    if (idx >= total * 32) return;
+    const int token = idx >> 5, k = idx & 31, m = k >> 2, p = k & 3;
+    const int N = H * W, n = token % N, i = n / W, j = n - i * W;
+    uint32_t s = seed ^ (uint32_t)idx * 2654435761u;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return (s >> 8) * (1.0f / 16777216.0f); };
+    const float u1 = fmaxf(rnd(), 1e-7f), u2 = rnd();
+    const float g0 = sqrtf(-2.f * logf(u1)) * cosf(6.2831853f * u2), g1 = sqrtf(-2.f * logf(u1)) * sinf(6.2831853f * u2);
+    const float th = 6.2831853f * m / 8.f;
+    float cx = cosf(th), cy = sinf(th);
+    const float mx = fmaxf(fabsf(cx), fabsf(cy));
+    cx /= mx; cy /= mx;
+    const float offx = cx * (p + 1) + sigma * g0, offy = cy * (p + 1) + sigma * g1;
+    const float refx = __fdiv_rn((float)j + 0.5f, (float)W), refy = __fdiv_rn((float)i + 0.5f, (float)H);
+    uint32_t word; float fx, fy;
+    msda_resolve(offx, offy, refx, refy, __frcp_rn((float)W), __frcp_rn((float)H), H, W, word, fx, fy);
+    uint32_t* rp = rec + (size_t)token * kRecW;
+    rp[k] = word;
+    reinterpret_cast<float*>(rp)[32 + k] = fx;
+    reinterpret_cast<float*>(rp)[64 + k] = fy;
+    reinterpret_cast<float*>(rp)[96 + k] = 0.25f + 0.1f * (rnd() - 0.5f);
+}
+
+template <class F>
+float time_ms(F launch, int reps) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 3; ++i) launch();
+    cudaDeviceSynchronize();
+    cudaEventRecord(a);
+    for (int i = 0; i < reps; ++i) launch();
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms / reps;
+}
+
+int main(int argc, char** argv) {
+    const int rows = 8, H = 128, W = 256, N = H * W, total = rows * N;
+    const float sigma = argc > 1 ? (float)atof(argv[1]) : 0.5f;
+    float* V; uint32_t* rec; __half *hi0, *lo0, *hi1, *lo1;
+    cudaMalloc(&V, (size_t)total * kE * 4); cudaMalloc(&rec, (size_t)total * kRecW * 4);
+    cudaMalloc(&hi0, (size_t)total * kE * 2); cudaMalloc(&lo0, (size_t)total * kE * 2);
+    cudaMalloc(&hi1, (size_t)total * kE * 2); cudaMalloc(&lo1, (size_t)total * kE * 2);
+    {
+        std::vector<float> h((size_t)total * kE);
+        srand(3);
+        for (auto& v : h) v = (rand() % 2001 - 1000) / 500.0f;
+        cudaMemcpy(V, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    }
+    k_make_records<<<(total * 32 + 255) / 256, 256>>>(rec, H, W, total, sigma, 12345u);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("record setup failed\n"); return 1; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int n_tiles = rows * (H / 8) * (W / 8);
+    for (int z = 0; z < 2; ++z) {         // both tile orders must visit every tile exactly once
+        std::vector<char> seen(n_tiles, 0);
+        for (int t = 0; t < n_tiles; ++t) {
+            int row, ti, tj;
+            if (z) tile_origin<true>(t, W / 8, H / 8, row, ti, tj); else tile_origin<false>(t, W / 8, H / 8, row, ti, tj);
+            const int id = (row * (H / 8) + ti) * (W / 8) + tj;
+            if (ti < 0 || ti >= H / 8 || tj < 0 || tj >= W / 8 || seen[id]) { printf("tile order %d is not a bijection at t = %d\n", z, t); return 1; }
+            seen[id] = 1;
+        }
+    }
+    const double gb = (double)total * (kE * 4 + kRecW * 4 + 2 * kE * 2) / 1e9;       // algorithmic HBM bytes
+
+    auto v0 = [&]() { k_msda_gather<<<(unsigned)(((size_t)total * 32 + 255) / 256), 256>>>(V, rec, nullptr, hi0, lo0, N, W, total); };
+    const float ms0 = time_ms(v0, 20);
+    printf("sigma %.2f px   v0 product kernel                       %.3f ms  (%.0f GB/s algorithmic)\n", sigma, ms0, gb / (ms0 / 1e3));
+    std::vector<uint16_t> ref((size_t)total * kE), got((size_t)total * kE);
+    cudaMemcpy(ref.data(), hi0, ref.size() * 2, cudaMemcpyDeviceToHost);
+    int rc = 0;
+    auto run = [&](const char* name, auto kern) {
+        for (int k : {1, 2, 4}) {
+            const int grid = sms * k;
+            cudaMemset(hi1, 0, (size_t)total * kE * 2);
+            auto l = [&]() { kern<<<grid, 256>>>(V, rec, hi1, lo1, H, W, n_tiles); };
+            const float ms = time_ms(l, 20);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaMemcpy(got.data(), hi1, got.size() * 2, cudaMemcpyDeviceToHost);
+            size_t bad = 0;
+            for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+            printf("               %-32s %d CTA/SM  %.3f ms  (%.2fx of v0)  %s%s\n", name, k, ms, ms0 / ms,
+                   bad ? "OUTPUT DIFFERS " : "bit-identical ", e == cudaSuccess ? "" : cudaGetErrorString(e));
+            if (bad || e != cudaSuccess) rc = 2;
+        }
+    };
+    run("v1 persistent, row-major tiles", k_gather_tiled<false, false>);
+    run("v2 persistent, Z-order tiles", k_gather_tiled<true, false>);
+    run("v3 Z-order, head-group major", k_gather_tiled<true, true>);
+    return rc;
+}
