@@ -106,6 +106,18 @@ struct ddp_handle {
     std::vector<Override> overrides;
     int64_t launches = 0;
 
+    // DDP_B200_GRAPH=1 (opt-in latency mode): the launch sequence of ddp_sample captured once per buffer set and replayed
+    struct GraphKey {
+        const void *x = nullptr, *noise = nullptr, *out = nullptr, *cls = nullptr, *ws = nullptr, *stream = nullptr;
+        bool operator==(const GraphKey& o) const {
+            return x == o.x && noise == o.noise && out == o.out && cls == o.cls && ws == o.ws && stream == o.stream;
+        }
+    };
+    bool use_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key, graph_warm_key;
+    int64_t graph_launches = 0;
+
     // per-kernel-class device timing (ddp_profile_*)
     bool prof_on = false;
     std::vector<ProfRec> prof;
@@ -605,6 +617,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* gr = getenv("DDP_B200_GRAPH");
+        h->use_graph = gr != nullptr && atoi(gr) != 0;                  // default off
         const char* d = getenv("DDP_B200_FFN_DBG");
         if (d && atoi(d) != 0 && cudaMalloc(&h->ffn_dbg, 64) == cudaSuccess) cudaMemset(h->ffn_dbg, 0, 64);
     }
@@ -624,6 +638,7 @@ void ddp_destroy(ddp_handle* h) {
         if (s.dev) cudaFree(s.dev);
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& e : h->ev_pool) cudaEventDestroy(e);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->w_arena) cudaFree(h->w_arena);
     if (h->tc_arena) cudaFree(h->tc_arena);
     if (h->p_arena) cudaFree(h->p_arena);
@@ -731,6 +746,8 @@ int ddp_commit_weights(ddp_handle* h) {
     h->t_W3 = dev("time_mlp.3.weight"); h->t_b3 = dev("time_mlp.3.bias");
     if (h->tc && (rc = commit_tc_weights(h, st))) return rc;
     CUDA_TRY(h, cudaDeviceSynchronize());
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }      // captured launches are stale
+    h->graph_warm_key = ddp_handle::GraphKey();
     h->committed = true;
     h->planned = false;
     return DDP_OK;
@@ -828,6 +845,8 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     h->maps_ws = nullptr;
     h->ws_bytes = carve(h, nullptr, nullptr, &h->ws_compute_bytes);
     if (workspace_bytes) *workspace_bytes = h->ws_bytes;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }      // captured launches are stale
+    h->graph_warm_key = ddp_handle::GraphKey();
     h->planned = true;
     return DDP_OK;
 }
@@ -1036,8 +1055,70 @@ static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half
     return DDP_OK;
 }
 
+static int sample_impl(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+// DDP_B200_GRAPH=1: latency mode for small batches (the reference's own use is one image per GPU, where the ~27 launches
+// per DDIM step are a visible fraction of the step).  The first call with a given set of buffers runs normally (kernel
+// attributes, tensor maps); the second is captured into a CUDA graph; later calls replay it.  Anything that changes
+// what the launches would be (plan, weights, schedule, taps, overrides, profiling, ddpm step noise) bypasses or
+// invalidates the graph.  Off by default.
 int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
                size_t workspace_bytes, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    const bool plain = h->planned && x && noise && out && workspace && h->taps.empty() && h->overrides.empty() && !h->prof_on &&
+                       h->cfg.diffusion == DDP_DIFFUSION_DDIM;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the legacy default stream cannot be captured: graph mode needs a caller stream (torch: `with torch.cuda.stream(s)`)
+    if (!h->use_graph || !plain || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)
+        return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    int rc;
+    if (h->time_dirty) {           // new schedule: the captured kernel arguments are stale; the H2D of the time table is not capturable
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        if ((rc = compute_time_constants(h, st))) return rc;
+    }
+    ddp_handle::GraphKey key;
+    key.x = x; key.noise = noise; key.out = out; key.cls = cls; key.ws = workspace; key.stream = stream;
+    if (h->graph_exec && key == h->graph_key) {
+        CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
+        h->launches = h->graph_launches;
+        return DDP_OK;
+    }
+    if (!(key == h->graph_warm_key)) {          // first call with these buffers: ordinary launches
+        h->graph_warm_key = key;
+        return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    }
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        h->use_graph = false;
+        return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    }
+    rc = sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != DDP_OK || ce != cudaSuccess || graph == nullptr) {     // not capturable here: fall back to ordinary launches for good
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->use_graph = false;
+        return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+        h->graph_exec = nullptr;
+        h->use_graph = false;
+        cudaGetLastError();
+        return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    }
+    h->graph_key = key;
+    h->graph_launches = h->launches;
+    CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
+    return DDP_OK;
+}
+
+static int sample_impl(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
+                       size_t workspace_bytes, void* stream) {
     if (!h) return DDP_ERR_INVALID;
     if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_sample: call ddp_plan first");
     if (!x || !noise || !out || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_sample: null pointer");

@@ -139,9 +139,11 @@ class DecodeEngine:
         return (p + 255) // 256 * 256
 
     # ------------------------------------------------------------------ the hot path
-    def sample(self, x: torch.Tensor, noise: torch.Tensor, return_cls=False, step_noise: Optional[torch.Tensor] = None):
+    def sample(self, x: torch.Tensor, noise: torch.Tensor, return_cls=False, step_noise: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None):
         """x (B,256,h,w), noise (B,R,Cin,h,w): CUDA fp32 tensors -> out (B,C,h,w) [, cls (B,h,w) int32].
         diffusion='ddpm' also needs step_noise (T,B,R,256,h,w): what the reference draws with randn_like every step.
+        `out`: optional preallocated result buffer (stable addresses are what the DDP_B200_GRAPH=1 latency mode keys on).
 
         Asynchronous on torch's current stream."""
         if self.diffusion == "ddpm":
@@ -161,7 +163,10 @@ class DecodeEngine:
             out = torch.empty((0, self.num_classes, h, w), dtype=torch.float32, device=x.device)
             return (out, torch.empty((0, h, w), dtype=torch.int32, device=x.device)) if (return_cls and self.task == "seg") else out
         self.plan(B, R, h, w)
-        out = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=x.device)
+        elif tuple(out.shape) != (B, self.num_classes, h, w) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous CUDA fp32 tensor of shape {(B, self.num_classes, h, w)}")
         cls = torch.empty((B, h, w), dtype=torch.int32, device=x.device) if (return_cls and self.task == "seg") else None
         stream = torch.cuda.current_stream(x.device).cuda_stream
         self._check(self.lib.ddp_sample(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
