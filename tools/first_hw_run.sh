@@ -16,7 +16,7 @@ python __graft_entry__.py > "$OUT/build.log" 2>&1 || { echo "build failed"; tail
 # 1. the pending tests as ordinary tests (--runxfail), neck first
 T=600 run pending_neck python -m pytest tests/test_zz_gpu_neck.py -q --runxfail -rA
 T=600 run pending_bev python -m pytest tests/test_zzz_gpu_bev.py -q --runxfail -rA
-T=600 run pending_graph python -m pytest tests/test_zz_gpu_graph.py -q --runxfail -rA
+T=600 run pending_graph python -m pytest tests/test_zzzz_gpu_graph.py -q --runxfail -rA
 
 # 2. device timing of both rows
 T=300 run bench_neck python tools/bench_rows.py neck
