@@ -3,6 +3,7 @@
 
     python tools/bench_rows.py neck [--images 8] [--h 128 --w 256] [--channels 96 192 384 768] [--steps 10]
     python tools/bench_rows.py bev  [--images 1] [--randsteps 5] [--timesteps 3] [--feat 256] [--steps 5]
+    python tools/bench_rows.py latency [--timesteps 10] [--steps 20]     # one image per call, with / without DDP_B200_GRAPH
 
 Same timing rules as bench.py (>= 3 warm-up calls, CUDA events on the launching stream, synchronise on both sides,
 inputs resident in HBM and larger than L2 or an explicit L2 flush inside the timed region).  One JSON line per run.
@@ -87,6 +88,33 @@ def run_bev(a):
                       "l2": "flushed before every call"}))
 
 
+def run_latency(a):
+    """The reference's own operating point: one image per GPU (tools/test.py, samples_per_gpu=1).  Per-call latency of the
+    decode loop at the headline geometry with ordinary launches and with the CUDA-graph replay (DDP_B200_GRAPH=1)."""
+    from ddp_b200 import DecodeEngine, synthetic
+    W = synthetic.make_weights(task="seg", num_classes=19, seed=7)
+    x, noise = synthetic.make_inputs("seg", 1, 1, 128, 256, seed=3)
+    x, noise = x.cuda(), noise.cuda()
+    out = torch.empty(1, 19, 128, 256, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    res = {}
+    side = torch.cuda.Stream()
+    for name, env in (("launches", None), ("graph", "1")):
+        if env is None:
+            os.environ.pop("DDP_B200_GRAPH", None)
+        else:
+            os.environ["DDP_B200_GRAPH"] = env
+        eng = DecodeEngine(task="seg", num_classes=19, timesteps=a.timesteps, gemm_mode="tc_3xf16")
+        eng.load_state_dict(W)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):                       # graph capture needs a non-default stream
+            res[name] = timed(lambda: eng.sample(x, noise, out=out), a.steps, flush)
+        res[name + "_launches_per_call"] = eng.last_launch_count
+    print(json.dumps({"row": "decode loop, one image per call (latency mode)", "tokens": [128, 256], "timesteps": a.timesteps,
+                      "ms_per_image_launches": res["launches"], "ms_per_image_graph": res["graph"],
+                      "launches_per_call": res["launches_launches_per_call"], "l2": "flushed before every call"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     sub = ap.add_subparsers(dest="row", required=True)
@@ -103,9 +131,12 @@ def main():
     b.add_argument("--feat", type=int, default=256)
     b.add_argument("--gemm", default="tc_3xf16", choices=["fp32", "tc_3xf16", "tc_f16"])
     b.add_argument("--steps", type=int, default=5)
+    lt = sub.add_parser("latency")
+    lt.add_argument("--timesteps", type=int, default=10)
+    lt.add_argument("--steps", type=int, default=20)
     a = ap.parse_args()
     torch.cuda.set_device(0)
-    {"neck": run_neck, "bev": run_bev}[a.row](a)
+    {"neck": run_neck, "bev": run_bev, "latency": run_latency}[a.row](a)
 
 
 if __name__ == "__main__":

@@ -22,6 +22,8 @@ T=600 run pending_graph python -m pytest tests/test_zzzz_gpu_graph.py -q --runxf
 T=300 run bench_neck python tools/bench_rows.py neck
 T=300 run bench_bev python tools/bench_rows.py bev
 T=300 run bench_bev_fusion python tools/bench_rows.py bev --feat 512
+T=300 run bench_latency_T10 python tools/bench_rows.py latency --timesteps 10
+T=300 run bench_latency_T3 python tools/bench_rows.py latency --timesteps 3
 
 # 3. micro-benchmarks behind the round-2 kernel plan (built here if the binaries did not travel)
 for u in ubench_gather ubench_sw_a; do
