@@ -23,7 +23,7 @@ EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "dd
            "ddp_weight_name", "ddp_set_weight", "ddp_commit_weights", "ddp_set_schedule",
            "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_head_forward", "ddp_resize_argmax", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
-           "ddp_profile_collect", "ddp_kernel_class_name",
+           "ddp_profile_collect", "ddp_kernel_class_name", "ddp_graph_replays", "ddp_graph_captures", "ddp_graph_last_fallback",
            "ddp_neck_create", "ddp_neck_destroy", "ddp_neck_last_error", "ddp_neck_weight_count", "ddp_neck_weight_name",
            "ddp_neck_set_weight", "ddp_neck_commit_weights", "ddp_neck_plan", "ddp_neck_forward",
            "ddp_neck_last_launch_count",
@@ -104,6 +104,12 @@ def load():
     lib.ddp_clear_debug.argtypes = [vp]
     lib.ddp_last_launch_count.argtypes = [vp]
     lib.ddp_last_launch_count.restype = i64
+    lib.ddp_graph_replays.argtypes = [vp]
+    lib.ddp_graph_replays.restype = i64
+    lib.ddp_graph_captures.argtypes = [vp]
+    lib.ddp_graph_captures.restype = i64
+    lib.ddp_graph_last_fallback.argtypes = [vp]
+    lib.ddp_graph_last_fallback.restype = cp
     lib.ddp_profile_enable.argtypes = [vp, i32]
     lib.ddp_profile_collect.argtypes = [vp, fp, ctypes.POINTER(i64), i32]
     lib.ddp_kernel_class_name.argtypes = [i32]

@@ -17,6 +17,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import schedule as S
+from ._stale import fingerprint
 from .models.ddp import LearnedSinusoidalPosEmb, _ConvModule1x1
 from .models.deformable_head_with_time import _EncoderParams, _MSDeformAttnParams
 from .registry import Registry
@@ -93,7 +94,10 @@ class BevDecodeEngine:
     def weight_names(self):
         out, n = {}, ctypes.c_int64()
         for i in range(self.lib.ddp_bev_weight_count(self._h)):
-            out[self.lib.ddp_bev_weight_name(self._h, i, ctypes.byref(n)).decode()] = n.value
+            # two statements on purpose: `out[f(byref(n))] = n.value` reads n.value BEFORE the call (Python evaluates the
+            # right-hand side first) — the round-1 bug that failed every neck / BEV hardware test
+            name = self.lib.ddp_bev_weight_name(self._h, i, ctypes.byref(n)).decode()
+            out[name] = n.value
         return out
 
     def load_state_dict(self, sd: Mapping[str, torch.Tensor]):
@@ -233,7 +237,8 @@ class BevDDP(nn.Module):
         self._engine = None
 
     def engine(self) -> BevDecodeEngine:
-        if self._engine is None:
+        fp = fingerprint(self)
+        if self._engine is None or fp != getattr(self, "_engine_fp", None):
             head = self.heads["map"]
             eng = BevDecodeEngine(timesteps=self.timesteps, time_difference=self.time_difference,
                                   noise_schedule=self.noise_schedule, diffusion=self.diffusion, bit_scale=self.bit_scale,
@@ -241,7 +246,7 @@ class BevDDP(nn.Module):
                                   learned_sinusoidal_dim=self.learned_sinusoidal_dim, num_layers=head.encoder.num_layers,
                                   sample_range=self.sample_range, gemm_mode=self.gemm_mode)
             eng.load_state_dict(self.state_dict())
-            self._engine = eng
+            self._engine, self._engine_fp = eng, fp
         return self._engine
 
     def refresh_engine(self):

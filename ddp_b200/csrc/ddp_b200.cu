@@ -117,6 +117,8 @@ struct ddp_handle {
     cudaGraphExec_t graph_exec = nullptr;
     GraphKey graph_key, graph_warm_key;
     int64_t graph_launches = 0;
+    int64_t graph_replays = 0, graph_captures = 0;      // ddp_graph_replays / ddp_graph_captures
+    std::string graph_fallback;                         // why the last ddp_sample did not replay a graph ("" = it did)
 
     // per-kernel-class device timing (ddp_profile_*)
     bool prof_on = false;
@@ -1063,6 +1065,17 @@ static int sample_impl(ddp_handle* h, const float* x, const float* noise, float*
 // attributes, tensor maps); the second is captured into a CUDA graph; later calls replay it.  Anything that changes
 // what the launches would be (plan, weights, schedule, taps, overrides, profiling, ddpm step noise) bypasses or
 // invalidates the graph.  Off by default.
+// graph mode gave up for this handle: say so once on stderr (a silent fallback made the latency numbers ambiguous)
+static int graph_give_up(ddp_handle* h, const char* why, cudaError_t e) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", why, cudaGetErrorString(e));
+    h->graph_fallback = buf;
+    h->use_graph = false;
+    fprintf(stderr, "[ddp_b200] DDP_B200_GRAPH=1: %s; this handle uses ordinary launches from now on\n", buf);
+    cudaGetLastError();
+    return DDP_OK;
+}
+
 int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
                size_t workspace_bytes, void* stream) {
     if (!h) return DDP_ERR_INVALID;
@@ -1070,8 +1083,13 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
                        h->cfg.diffusion == DDP_DIFFUSION_DDIM;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the legacy default stream cannot be captured: graph mode needs a caller stream (torch: `with torch.cuda.stream(s)`)
-    if (!h->use_graph || !plain || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread)
+    if (!h->use_graph || !plain || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+        if (h->use_graph) h->graph_fallback = !plain ? "taps / overrides / profiling / ddpm / missing plan bypass the graph"
+                                                     : "the legacy default stream cannot be captured";
         return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
+    }
+    if (workspace_bytes < h->ws_compute_bytes)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample: workspace %zu < required %zu", workspace_bytes, h->ws_compute_bytes);
     int rc;
     if (h->time_dirty) {           // new schedule: the captured kernel arguments are stale; the H2D of the time table is not capturable
         if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -1082,40 +1100,48 @@ int ddp_sample(ddp_handle* h, const float* x, const float* noise, float* out, in
     if (h->graph_exec && key == h->graph_key) {
         CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
         h->launches = h->graph_launches;
+        h->graph_replays++;
+        h->graph_fallback.clear();
         return DDP_OK;
     }
     if (!(key == h->graph_warm_key)) {          // first call with these buffers: ordinary launches
         h->graph_warm_key = key;
+        h->graph_fallback = "first call with this buffer set (warm-up, ordinary launches)";
         return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
     }
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-        cudaGetLastError();
-        h->use_graph = false;
+    cudaError_t ce = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) {
+        graph_give_up(h, "cudaStreamBeginCapture failed", ce);
         return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
     }
     rc = sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    ce = cudaStreamEndCapture(st, &graph);
     if (rc != DDP_OK || ce != cudaSuccess || graph == nullptr) {     // not capturable here: fall back to ordinary launches for good
         if (graph) cudaGraphDestroy(graph);
-        cudaGetLastError();
-        h->use_graph = false;
+        graph_give_up(h, rc != DDP_OK ? "a launch failed under stream capture" : "cudaStreamEndCapture failed", ce);
         return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
     }
     const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ie != cudaSuccess) {
         h->graph_exec = nullptr;
-        h->use_graph = false;
-        cudaGetLastError();
+        graph_give_up(h, "cudaGraphInstantiate failed", ie);
         return sample_impl(h, x, noise, out, cls, workspace, workspace_bytes, stream);
     }
     h->graph_key = key;
     h->graph_launches = h->launches;
+    h->graph_captures++;
     CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
+    h->graph_replays++;
+    h->graph_fallback.clear();
     return DDP_OK;
 }
+
+int64_t ddp_graph_replays(const ddp_handle* h) { return h ? h->graph_replays : 0; }
+int64_t ddp_graph_captures(const ddp_handle* h) { return h ? h->graph_captures : 0; }
+const char* ddp_graph_last_fallback(const ddp_handle* h) { return h ? h->graph_fallback.c_str() : ""; }
 
 static int sample_impl(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
                        size_t workspace_bytes, void* stream) {

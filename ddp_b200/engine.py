@@ -157,6 +157,7 @@ class DecodeEngine:
         R = noise.shape[1]
         assert c == EMBED and tuple(noise.shape) == (B, R, self.cin, h, w), (x.shape, noise.shape)
         assert x.is_cuda and noise.is_cuda and x.dtype == torch.float32 and noise.dtype == torch.float32
+        self._on_device(x, noise, out)
         x = x.contiguous()
         noise = noise.contiguous()
         if B == 0:                      # empty batch: nothing to launch (the C ABI itself rejects B < 1)
@@ -169,9 +170,10 @@ class DecodeEngine:
             raise ValueError(f"out must be a contiguous CUDA fp32 tensor of shape {(B, self.num_classes, h, w)}")
         cls = torch.empty((B, h, w), dtype=torch.int32, device=x.device) if (return_cls and self.task == "seg") else None
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        self._check(self.lib.ddp_sample(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
-                                        cls.data_ptr() if cls is not None else None,
-                                        self._ws_ptr(), self._ws_bytes, stream))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_sample(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                                            cls.data_ptr() if cls is not None else None,
+                                            self._ws_ptr(), self._ws_bytes, stream))
         return (out, cls) if return_cls else out
 
     def head_forward(self, feat: torch.Tensor, time_embedding: torch.Tensor):
@@ -179,6 +181,7 @@ class DecodeEngine:
         rows must be B*R of the current plan (plan(rows, 1, h, w) is made if there is none that fits)."""
         rows, c, h, w = feat.shape
         assert c == EMBED and feat.is_cuda and feat.dtype == torch.float32
+        self._on_device(feat)
         if self._plan is None or self._plan[0] * self._plan[1] != rows or self._plan[2:] != (h, w):
             self.plan(rows, 1, h, w)
         feat = feat.contiguous()
@@ -186,18 +189,21 @@ class DecodeEngine:
         assert temb.numel() == 4 * EMBED
         out = torch.empty((rows, self.num_classes, h, w), dtype=torch.float32, device=feat.device)
         stream = torch.cuda.current_stream(feat.device).cuda_stream
-        self._check(self.lib.ddp_head_forward(self._h, feat.data_ptr(), temb.data_ptr(), out.data_ptr(),
-                                              self._ws_ptr(), self._ws_bytes, stream))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_head_forward(self._h, feat.data_ptr(), temb.data_ptr(), out.data_ptr(),
+                                                  self._ws_ptr(), self._ws_bytes, stream))
         return out
 
     def resize_argmax(self, logits: torch.Tensor, size):
         """(B,C,h,w) logits -> uint8 class map (B,H,W): bilinear resize + softmax + argmax in one kernel."""
         B, C, h, w = logits.shape
         H, W = int(size[0]), int(size[1])
+        self._on_device(logits)
         logits = logits.contiguous()
         cls = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
         stream = torch.cuda.current_stream(logits.device).cuda_stream
-        self._check(self.lib.ddp_resize_argmax(self._h, logits.data_ptr(), B, C, h, w, H, W, cls.data_ptr(), stream))
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_resize_argmax(self._h, logits.data_ptr(), B, C, h, w, H, W, cls.data_ptr(), stream))
         return cls
 
     def sample_host(self, x: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None,
@@ -221,6 +227,26 @@ class DecodeEngine:
     @property
     def last_launch_count(self):
         return int(self.lib.ddp_last_launch_count(self._h))
+
+    @property
+    def graph_replays(self):
+        """DDP_B200_GRAPH=1 latency mode: sample() calls served by replaying the captured CUDA graph so far."""
+        return int(self.lib.ddp_graph_replays(self._h))
+
+    @property
+    def graph_captures(self):
+        return int(self.lib.ddp_graph_captures(self._h))
+
+    @property
+    def graph_last_fallback(self):
+        """Why the last sample() used ordinary launches ('' when it replayed the graph)."""
+        return self.lib.ddp_graph_last_fallback(self._h).decode()
+
+    def _on_device(self, *tensors):
+        """The handle is bound to self.device: reject tensors of another GPU instead of launching into the wrong context."""
+        for t in tensors:
+            if t is not None and t.device != self.device:
+                raise ValueError(f"tensor on {t.device}, this engine is bound to {self.device}")
 
     def profile(self, on=True):
         """Bracket every kernel launch of sample() with CUDA events (per kernel class)."""

@@ -12,10 +12,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .._stale import fingerprint
 from ..engine import DecodeEngine
 from ..registry import SEGMENTORS, MODELS, build_head
 
 EMBED = 256
+_COLD_PREFIXES = ("backbone.", "neck.", "auxiliary_head.")      # not weights of the decode loop
 
 
 def resize(input, size=None, scale_factor=None, mode="nearest", align_corners=None, warning=True):
@@ -93,18 +95,18 @@ class _DiffusionSegmentorBase(nn.Module):
 
     # ---- engine management -----------------------------------------------------------------
     def _hot_state_dict(self):
-        return {k: v for k, v in self.state_dict().items()
-                if not k.startswith(("backbone.", "neck.", "auxiliary_head."))}
+        return {k: v for k, v in self.state_dict().items() if not k.startswith(_COLD_PREFIXES)}
 
     def _engine_kwargs(self):
         raise NotImplementedError
 
     def engine(self) -> DecodeEngine:
         """The CUDA decode engine bound to the current parameters (rebuilt after load_state_dict / refresh)."""
-        if self._engine is None:
+        fp = fingerprint(self, _COLD_PREFIXES)
+        if self._engine is None or fp != getattr(self, "_engine_fp", None):
             eng = DecodeEngine(gemm_mode=self.gemm_mode, **self._engine_kwargs())
             eng.load_state_dict(self._hot_state_dict())
-            self._engine = eng
+            self._engine, self._engine_fp = eng, fp
         return self._engine
 
     def refresh_engine(self):
@@ -259,7 +261,9 @@ class DDP(_DiffusionSegmentorBase):
 
     def simple_test(self, img, img_meta, rescale=True):
         meta = img_meta[0]
-        plain = (not meta.get("flip", False) and (self.test_cfg or {}).get("mode", "whole") == "whole"
+        # k_resize_argmax implements the align_corners=False source-index mapping (every DDP config); a head configured
+        # with align_corners=True takes the unfused path below, which honours the flag (encoder_decoder.py:241-249)
+        plain = (not self.align_corners and not meta.get("flip", False) and (self.test_cfg or {}).get("mode", "whole") == "whole"
                  and tuple(meta.get("img_shape", ())[:2]) == tuple(img.shape[2:])
                  and (not rescale or tuple(meta.get("ori_shape", ())[:2]) == tuple(img.shape[2:])))
         if self.fused_tail and plain and self.diffusion == "ddim":

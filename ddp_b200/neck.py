@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from ._stale import fingerprint
 from .registry import NECKS
 
 OUT = 256
@@ -62,7 +63,10 @@ class NeckEngine:
     def weight_names(self):
         out, n = {}, ctypes.c_int64()
         for i in range(self.lib.ddp_neck_weight_count(self._h)):
-            out[self.lib.ddp_neck_weight_name(self._h, i, ctypes.byref(n)).decode()] = n.value
+            # two statements on purpose: `out[f(byref(n))] = n.value` reads n.value BEFORE the call (Python evaluates the
+            # right-hand side first) — the round-1 bug that failed every neck / BEV hardware test
+            name = self.lib.ddp_neck_weight_name(self._h, i, ctypes.byref(n)).decode()
+            out[name] = n.value
         return out
 
     def load_state_dict(self, sd: Mapping[str, torch.Tensor]):
@@ -166,10 +170,11 @@ class _NeckModule(nn.Module):
         return self.state_dict()
 
     def engine(self) -> NeckEngine:
-        if self._engine is None:
+        fp = fingerprint(self)
+        if self._engine is None or fp != getattr(self, "_engine_fp", None):
             eng = NeckEngine(self._engine_in_channels(), stages=self._stages, num_groups=self._groups)
             eng.load_state_dict(self._engine_state())
-            self._engine = eng
+            self._engine, self._engine_fp = eng, fp
         return self._engine
 
     def refresh_engine(self):

@@ -180,6 +180,16 @@ int ddp_clear_debug(ddp_handle* h);
 /* Number of kernel launches the last ddp_sample enqueued (for bench.py's gpu_launches). */
 int64_t ddp_last_launch_count(const ddp_handle* h);
 
+/* Latency mode (environment DDP_B200_GRAPH=1 at ddp_create; the reference's own deployment is one image per GPU,
+ * segmentation/tools/test.py:216, tools/benchmark.py:62): ddp_sample's launch sequence is captured into a CUDA graph on the
+ * second call with one buffer set + caller stream and replayed afterwards.  ddp_graph_replays = calls served by
+ * cudaGraphLaunch so far, ddp_graph_captures = graphs instantiated so far, ddp_graph_last_fallback = why the LAST
+ * ddp_sample used ordinary launches ("" when it replayed).  A capture / instantiate failure switches the mode off for the
+ * handle and says so once on stderr. */
+int64_t ddp_graph_replays(const ddp_handle* h);
+int64_t ddp_graph_captures(const ddp_handle* h);
+const char* ddp_graph_last_fallback(const ddp_handle* h);
+
 /* Per-kernel-class device timing: while enabled, every launch of ddp_sample is bracketed by CUDA
  * events on the launching stream; ddp_profile_collect waits for them and returns, per class, the
  * summed milliseconds and the number of launches since the last collect. */

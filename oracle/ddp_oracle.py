@@ -28,6 +28,7 @@ Reference file:line followed by each function (paths relative to
   encoder_layer         segmentation/mmseg/models/utils/transformer.py:374-419
   head_tokens / head_seg segmentation/mmseg/models/decode_heads/deformable_head_with_time.py:90-132
   ddim_sample_seg       segmentation/mmseg/models/segmentors/ddp.py:215-246
+  step_seg_one          segmentation/mmseg/models/segmentors/ddp.py:222-245 (one loop iteration; ddpm: 255-287)
   ddpm_sample_seg       segmentation/mmseg/models/segmentors/ddp.py:248-290
   time_pairs_depth      depth/depth/models/depther/ddp.py:210-218
   gamma_depth           depth/depth/models/depther/ddp.py:207-208
@@ -346,55 +347,74 @@ def _rows(x, R):
     return x.repeat(R, 1, 1, 1)
 
 
+def step_seg_one(W, cfg: OracleConfig, xr, mask_t, idx, ddpm_noise_k=None, taps=None, sched_dtype=None):
+    """ONE iteration of the reference loop body (ddp.py:222-245; ddpm: 255-287) for one image: xr (R,256,h,w) the
+    repeated feature, mask_t (R,256,h,w) the state ENTERING step idx -> dict(logits, state, feat, temb, argmax, sched).
+    `_sample_seg_one` is this function in a loop; the closed-loop parity check (tests/parity.py) calls it with the
+    CUDA path's own state.  sched_dtype=torch.float32 with float64 tensors evaluates the schedule scalars (ill-conditioned
+    in fp32) exactly as the fp32 reference does and everything downstream in float64 — the adjudicator."""
+    dtype = xr.dtype
+    sd = dtype if sched_dtype is None else sched_dtype
+    log_snr_fn = log_snr_cosine if cfg.noise_schedule == "cosine" else log_snr_linear
+    if cfg.noise_schedule not in ("cosine", "linear"):
+        raise ValueError(f"invalid noise schedule {cfg.noise_schedule}")
+    t_now, t_next = time_pairs_seg(cfg)[idx]
+    times = torch.tensor([t_now, t_next], device=xr.device)          # float32, as in the reference
+    times_now = times[0:1].to(sd)
+    times_next = times[1:2].to(sd)
+    feat = torch.cat([xr, mask_t], dim=1)
+    feat = F.conv2d(feat, W["transform.conv.weight"], W["transform.conv.bias"])
+    log_snr = log_snr_fn(times_now)
+    log_snr_next = log_snr_fn(times_next)
+    alpha, sigma = alpha_sigma(log_snr.view(1, 1, 1, 1))
+    alpha_next, sigma_next = alpha_sigma(log_snr_next.view(1, 1, 1, 1))
+    if sd != dtype:
+        log_snr, log_snr_next = log_snr.to(dtype), log_snr_next.to(dtype)
+        alpha, sigma, alpha_next, sigma_next = (v.to(dtype) for v in (alpha, sigma, alpha_next, sigma_next))
+    temb = time_mlp(W, log_snr)
+    mask_logit = head_seg(W, cfg, feat, temb, taps)
+    pred_idx = torch.argmax(mask_logit, dim=1)
+    mask_pred = F.embedding(pred_idx, W["embedding_table.weight"]).permute(0, 3, 1, 2)
+    mask_pred = (torch.sigmoid(mask_pred) * 2 - 1) * cfg.bit_scale
+    if cfg.diffusion == "ddim":
+        pred_noise = (mask_t - alpha * mask_pred) / sigma.clamp(min=1e-8)
+        mask_t = mask_pred * alpha_next + pred_noise * sigma_next
+    elif cfg.diffusion == "ddpm":
+        c = -torch.special.expm1(log_snr - log_snr_next)
+        mean = alpha_next * (mask_t * (1 - c) / alpha + c * mask_pred)
+        variance = (sigma_next ** 2) * c
+        log_variance = _log(variance)
+        nz = ddpm_noise_k if t_next > 0 else torch.zeros_like(mask_t)
+        mask_t = mean + (0.5 * log_variance).exp() * nz
+    else:
+        raise NotImplementedError
+    return dict(logits=mask_logit, state=mask_t, feat=feat, temb=temb, argmax=pred_idx,
+                sched=tuple(float(v) for v in (log_snr, alpha, sigma, alpha_next, sigma_next)))
+
+
 def _sample_seg_one(W, cfg: OracleConfig, x, noise, trace: Optional[Trace], ddpm_noise=None):
     """x (1,256,h,w); noise (R,256,h,w) -> (1,C,h,w).  Reference semantics (b=1)."""
-    dtype = x.dtype
     R = noise.shape[0]
-    log_snr_fn = log_snr_cosine if cfg.noise_schedule == "cosine" else log_snr_linear
     if cfg.noise_schedule not in ("cosine", "linear"):
         raise ValueError(f"invalid noise schedule {cfg.noise_schedule}")
     xr = _rows(x, R)
     mask_t = noise
     outs = []
     mask_logit = None
-    for idx, (t_now, t_next) in enumerate(time_pairs_seg(cfg)):
-        times = torch.tensor([t_now, t_next], device=x.device)          # float32, as in the reference
-        times_now = times[0:1].to(dtype)
-        times_next = times[1:2].to(dtype)
-        feat = torch.cat([xr, mask_t], dim=1)
-        feat = F.conv2d(feat, W["transform.conv.weight"], W["transform.conv.bias"])
-        log_snr = log_snr_fn(times_now)
-        log_snr_next = log_snr_fn(times_next)
-        alpha, sigma = alpha_sigma(log_snr.view(1, 1, 1, 1))
-        alpha_next, sigma_next = alpha_sigma(log_snr_next.view(1, 1, 1, 1))
-        temb = time_mlp(W, log_snr)
+    for idx in range(len(time_pairs_seg(cfg))):
         taps = [] if trace is not None else None
-        mask_logit = head_seg(W, cfg, feat, temb, taps)
-        pred_idx = torch.argmax(mask_logit, dim=1)
-        mask_pred = F.embedding(pred_idx, W["embedding_table.weight"]).permute(0, 3, 1, 2)
-        mask_pred = (torch.sigmoid(mask_pred) * 2 - 1) * cfg.bit_scale
-        if cfg.diffusion == "ddim":
-            pred_noise = (mask_t - alpha * mask_pred) / sigma.clamp(min=1e-8)
-            mask_t = mask_pred * alpha_next + pred_noise * sigma_next
-        elif cfg.diffusion == "ddpm":
-            c = -torch.special.expm1(log_snr - log_snr_next)
-            mean = alpha_next * (mask_t * (1 - c) / alpha + c * mask_pred)
-            variance = (sigma_next ** 2) * c
-            log_variance = _log(variance)
-            nz = ddpm_noise[idx] if t_next > 0 else torch.zeros_like(mask_t)
-            mask_t = mean + (0.5 * log_variance).exp() * nz
-        else:
-            raise NotImplementedError
+        st = step_seg_one(W, cfg, xr, mask_t, idx, None if ddpm_noise is None else ddpm_noise[idx], taps)
+        mask_logit, mask_t = st["logits"], st["state"]
         if cfg.accumulation:
             outs.append(mask_logit.softmax(1))
         if trace is not None:
-            trace.feat.append(feat)
-            trace.temb.append(temb)
+            trace.feat.append(st["feat"])
+            trace.temb.append(st["temb"])
             trace.layers.append(taps)
             trace.logits.append(mask_logit)
-            trace.argmax.append(pred_idx)
+            trace.argmax.append(st["argmax"])
             trace.mask_t.append(mask_t)
-            trace.sched.append(tuple(float(v) for v in (log_snr, alpha, sigma, alpha_next, sigma_next)))
+            trace.sched.append(st["sched"])
     if cfg.accumulation:
         mask_logit = torch.cat(outs, dim=0)
     return mask_logit.mean(dim=0, keepdim=True)

@@ -14,8 +14,7 @@ import torch
 from oracle import neck_oracle as NO
 from golden_util import golden_files, load_neck_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.first_hw_run(reason="neck kernels: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 
 TOL = 5e-5     # fp32 summation order (K up to 2304) on O(1) GroupNorm outputs; the host emulation measures <= 1e-5
 CH = [96, 192, 384, 768]

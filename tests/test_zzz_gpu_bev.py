@@ -14,8 +14,7 @@ import torch
 from oracle import bev_oracle as BO
 from golden_util import golden_files, load_bev_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.first_hw_run(reason="BEV loop kernels: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 
 ATOL = 2e-4        # same fp32-summation-order tolerance as the segmentation path (values are probabilities here)
 

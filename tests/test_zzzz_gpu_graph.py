@@ -1,15 +1,13 @@
 """DDP_B200_GRAPH=1 (opt-in latency mode: the launch sequence of ddp_sample captured into a CUDA graph and replayed)
-must give the very bits of the ordinary launches.
-
-STATUS: written after the round-1 GPU budget was spent; the default path (graph mode off) is untouched by it.  Marked
-`first_hw_run` (collected last, non-strict xfail, tests/conftest.py) until a GPU run has confirmed it."""
+must give the very bits of the ordinary launches AND must really replay a graph: the replay / capture counters of the
+C ABI (ddp_graph_replays, ddp_graph_captures, ddp_graph_last_fallback) are asserted call by call, so a silent fall-back
+to ordinary launches fails the test."""
 import pytest
 import torch
 
 from oracle import ddp_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.first_hw_run(reason="CUDA-graph latency mode: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _engine(cfg, W, mode):
@@ -36,24 +34,31 @@ def test_graph_replay_equals_ordinary_launches(monkeypatch, task, mode):
     torch.cuda.synchronize()
     side = torch.cuda.Stream()               # the legacy default stream cannot be captured (graph mode bypasses itself there)
     with torch.cuda.stream(side):
-        for _ in range(4):                   # 1st call: ordinary launches, 2nd: capture + launch, 3rd / 4th: replay
+        for i in range(4):                   # 1st call: ordinary launches, 2nd: capture + launch, 3rd / 4th: replay
             out.zero_()
             eng.sample(x, n, out=out)
             side.synchronize()
             assert torch.equal(out, want1)
+            assert eng.graph_replays == (0, 1, 2, 3)[i], eng.graph_last_fallback
+            assert eng.graph_captures == (0, 1, 1, 1)[i], eng.graph_last_fallback
+            assert (eng.graph_last_fallback == "") == (i > 0)
         assert eng.last_launch_count == plain.last_launch_count
         x.copy_(x2.cuda()); n.copy_(n2.cuda())   # new data through the same buffers: the replay reads them
         eng.sample(x, n, out=out)
         side.synchronize()
         assert torch.equal(out, want2)
+        assert eng.graph_replays == 4 and eng.graph_captures == 1
         other = torch.empty_like(out)        # a different output buffer: ordinary launches again, then a new graph
-        for _ in range(3):
+        for i in range(3):
             eng.sample(x, n, out=other)
             side.synchronize()
             assert torch.equal(other, want2)
+            assert eng.graph_replays == 4 + i and eng.graph_captures == 1 + (i > 0), eng.graph_last_fallback
         eng.plan(1, 2, 12, 20)               # a new plan invalidates the graph
         got = eng.sample(x[:1].contiguous(), n[:1].contiguous())
         side.synchronize()
     assert torch.equal(got, plain.sample(x[:1].contiguous(), n[:1].contiguous()))
     # on the default stream graph mode steps aside and the ordinary launches run
+    before = eng.graph_replays
     assert torch.equal(eng.sample(x[:1].contiguous(), n[:1].contiguous()), got)
+    assert eng.graph_replays == before and "default stream" in eng.graph_last_fallback
