@@ -241,6 +241,202 @@ def workload_config(wl, name, global_batch, args):
                   % (wl["per_gpu"] * E * wl["h"] * wl["w"] * 4 / 1e6)}
 
 
+def measure(name, wl, args, ctx, steps, warmup, with_clocks=False):
+    """One workload on this rank's GPU: clean device-resident timing (profiling OFF), a second pass with per-launch events
+    for the kernel breakdown / roofline, the end-to-end pass through the host-buffer entry point, and (rank 0, N = 1) the two
+    reference legs: the reference's op sequence on the same GPU and on the host cores.  Returns the JSON fields."""
+    dev, world, rank, dist = ctx["dev"], ctx["world"], ctx["rank"], ctx["dist"]
+    from ddp_b200 import DecodeEngine
+    B = wl["per_gpu"]
+    W, x, noise = make_weights_and_inputs(wl, B, seed=1234 + rank)
+    eng = DecodeEngine(task=wl["task"], num_classes=wl["C"], timesteps=wl["T"], accumulation=wl["acc"],
+                       bit_scale=wl["bit_scale"], gemm_mode=args.gemm)
+    eng.load_state_dict(W)
+    xd, nd = x.to(dev), noise.to(dev)
+    xh, nh = x.pin_memory(), noise.pin_memory()
+    out_h = torch.empty((B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32).pin_memory()
+    gathered = local_out = None
+    if world > 1:
+        gathered = torch.empty((world * B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32, device=dev)
+        local_out = torch.empty((B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32, device=dev)
+
+    # timing rule: inputs larger than L2, or an explicit flush between iterations.  The default workload's x is 268 MB
+    # per rank; for the small ones (uncertainty: 67 MB, plumbing: 4 MB) a 256 MB buffer is overwritten before every step
+    # INSIDE the timed region (~0.05 ms per step).
+    x_bytes = B * E * wl["h"] * wl["w"] * 4
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if x_bytes < (192 << 20) else None
+
+    def step_device():
+        if flush_buf is not None:
+            flush_buf.zero_()
+        out = eng.sample(xd, nd)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)     # the single gather of final logits
+        return out
+
+    def step_e2e():
+        # synchronous host-buffer call: H2D x + noise, loop, D2H logits all inside, pipelined in two groups of images; at
+        # N > 1 the result also lands in `local_out`, the send buffer of the one gather
+        if flush_buf is not None:
+            flush_buf.zero_()
+        eng.sample_host(xh, nh, out=out_h, out_device=local_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, local_out)
+        return out_h
+
+    out_h2 = [out_h, torch.empty_like(out_h).pin_memory()]
+    local_out2 = [local_out, torch.empty_like(local_out) if local_out is not None else None]
+
+    def run_e2e_stream(n):
+        """n calls through the streaming host entry point (two in flight): every call uploads its x + noise from pinned
+        host memory and downloads its logits; the copies of call i+1 / i-1 overlap the loop of call i."""
+        prev = None
+        for i in range(n):
+            if flush_buf is not None:
+                flush_buf.zero_()
+            t = eng.submit_host(xh, nh, out_h2[i % 2], out_device=local_out2[i % 2])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local_out2[i % 2])
+            if prev is not None:
+                eng.wait_host(prev)
+            prev = t
+        eng.wait_host(prev)
+
+    def timed(fn, n, sampler=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms, clocks
+
+    # (1) the headline: W warm-up steps, then exactly K steps, profiling OFF, device time between two events, max over ranks
+    for _ in range(warmup):
+        step_device()
+    ms, clocks = timed(step_device, steps, ClockSampler(ctx["local"]) if (rank == 0 and with_clocks) else None)
+    launches = eng.last_launch_count
+    ms_per_step = ms / steps
+    value = world * B * steps / (ms / 1e3)
+
+    # (2) second pass: every launch bracketed by CUDA events on the launching stream -> per-class times, roofline
+    psteps = max(1, min(steps, 3))
+    eng.profile(True)
+    ms_prof, _ = timed(step_device, psteps)
+    prof = eng.profile_collect()
+    eng.profile(False)
+
+    # (3) end to end through the host-buffer entry points (pinned host x + noise in, logits out, every step):
+    #     `e2e` = the streaming form (ddp_sample_host_submit / _wait, two calls in flight), the sustained rate of a queue
+    #     of batches; `single_call` = one synchronous ddp_sample_host at a time (its own upload cannot hide)
+    step_e2e()
+    e2e_steps = max(1, min(steps, 3))
+    ms_e2e1, _ = timed(step_e2e, e2e_steps)
+    run_e2e_stream(2)
+    ms_e2e, _ = timed(lambda: run_e2e_stream(steps), 1)
+    e2e_value = world * B * steps / (ms_e2e / 1e3)
+    e2e1_value = world * B * e2e_steps / (ms_e2e1 / 1e3)
+    h2d = (xh.numel() + nh.numel()) * 4
+    d2h = out_h.numel() * 4
+    if rank != 0:
+        return None
+
+    peaks = load_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][0])          # dominant kernel class by device time
+    dname, (dms, dcount) = dom
+    tokens_per_launch = B * wl["R"] * wl["h"] * wl["w"]
+    fl, by = class_cost(dname, wl)
+    avg_s = dms / max(dcount, 1) / 1e3
+    gemm_like = dname not in ("msda_gather", "step_update", "finalize", "layout")
+    if gemm_like:
+        achieved = fl * tokens_per_launch / avg_s / 1e12
+        roof = {"bound": "tensor", "kernel": dname, "achieved": achieved, "peak": peaks["tensor_sustained"] or peaks["tensor"],
+                "unit": "TFLOP/s", "frac": achieved / (peaks["tensor_sustained"] or peaks["tensor"]),
+                "peak_source": peaks["source"] + " (bf16 dense, sustained)", "traffic": None}
+    else:
+        achieved = by * tokens_per_launch / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel class: ncu cannot run inside the bench, so this
+    # is the committed `ncu --set full` capture of the same command (profiles/ncu_traffic.json names the commit)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        t = tj.get(f"{name}/{args.gemm}", {}).get(dname)
+        if t is not None and wl["per_gpu"] == WORKLOADS[name]["per_gpu"]:
+            roof["traffic"] = t
+            roof["traffic_source"] = "profiles/ncu_traffic.json: " + str(tj.get("_source", "ncu --set full capture"))
+    roof["algorithmic_bytes"] = by * tokens_per_launch
+    roof["avg_launch_ms"] = 1e3 * avg_s
+    roof["launches_timed"] = dcount
+    total_prof = sum(v[0] for v in prof.values())
+    roof["share_of_step"] = dms / total_prof if total_prof else None
+    whole = world * B * steps * flops_per_image(wl) / (ms / 1e3) / 1e12
+    kernel_ms = {k: round(v[0] / psteps, 3) for k, v in prof.items() if v[1]}
+
+    res = {
+        "value": value, "unit": "images/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+        "config": workload_config(wl, name, world * B, args), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / steps, "steps": steps,
+                "api": "ddp_sample_host_submit/_wait (streaming, two calls in flight, pinned host buffers)",
+                "single_call": {"value": e2e1_value, "ms_per_step": ms_e2e1 / e2e_steps,
+                                "api": "ddp_sample_host (synchronous, batch pipelined in two groups)"}},
+        "gpu_launches": launches * steps, "launches_per_step": launches,
+        "roofline": roof, "whole_loop_tflops": whole,
+        "whole_loop_frac_of_tensor_peak": whole / (peaks["tensor_sustained"] or peaks["tensor"]),
+        "kernel_ms_per_step": kernel_ms, "profiled_pass_ms_per_step": ms_prof / psteps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        del eng, xd, nd, flush_buf
+        torch.cuda.empty_cache()
+        cfg = oracle_cfg(wl)
+        # the north star's own comparator: the reference's PyTorch op sequence on this same B200
+        res["gpu_reference"] = gpu_reference(cfg, wl, W, x[:1], noise[:1], dev)
+        cores, thread_log = pick_cpu_threads(cfg, W, x[:1], noise[:1])
+        nsteps = 2 if wl["h"] * wl["w"] * wl["R"] >= 16384 else min(wl["T"], 4)
+        t = cpu_reference_step(cfg, W, x[:1], noise[:1], nsteps)
+        cpu_value = 1.0 / (t / nsteps * wl["T"])
+        res["cpu_baseline"] = {"value": cpu_value, "unit": "images/s", "cores": cores, "kind": "port",
+                               "sample": f"oracle (PyTorch-CPU port pinned to the reference), 1 image, {nsteps} of {wl['T']} "
+                                         f"DDIM steps in {t:.1f} s, scaled to T={wl['T']}; torch threads chosen by timing one step "
+                                         f"each: {thread_log} s of {os.cpu_count()} cores"}
+    return res
+
+
+def gpu_reference(cfg, wl, W, x1, noise1, dev, steps=2):
+    """The reference's own PyTorch op sequence (oracle port) run eagerly on the same GPU, one image per call (the reference
+    loop is defined for b = 1), all T steps.  Its deformable attention goes through the grid_sample branch of mmcv's Python
+    fallback: mmcv-full's CUDA op is not installable here."""
+    from oracle import ddp_oracle as O
+    Wd = {k: v.to(dev) for k, v in W.items()}
+    xd, nd = x1.to(dev), noise1.to(dev)
+    O.sample(Wd, cfg, xd, nd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        O.sample(Wd, cfg, xd, nd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": 1e3 / ms, "unit": "images/s", "ms_per_image": ms,
+            "note": "oracle-on-GPU: the reference's PyTorch op sequence, eager, fp32, on the same B200, 1 image per call, all "
+                    f"{wl['T']} steps; deformable attention via grid_sample (mmcv's Python fallback), not mmcv-full's CUDA op"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -249,7 +445,8 @@ def main():
     ap.add_argument("--workload", default="cityscapes_512x1024_T10", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm", default=os.environ.get("DDP_GEMM", "tc_3xf16"), choices=["fp32", "tc_3xf16", "tc_f16"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and oracle-on-GPU reference legs")
+    ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE.json configs in the `also` block")
     ap.add_argument("--reference-device", default="cpu", choices=["cpu", "cuda"],
                     help="with --impl reference: cpu (default, the measurement contract) or cuda (oracle-on-GPU comparison)")
     ap.add_argument("--per-gpu", type=int, default=0, help="override images per GPU")
@@ -273,150 +470,33 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
+    ctx = dict(dev=dev, world=world, rank=rank, local=local, dist=dist)
 
-    from ddp_b200 import DecodeEngine
-    B = wl["per_gpu"]
-    W, x, noise = make_weights_and_inputs(wl, B, seed=1234 + rank)
-    eng = DecodeEngine(task=wl["task"], num_classes=wl["C"], timesteps=wl["T"], accumulation=wl["acc"],
-                       bit_scale=wl["bit_scale"], gemm_mode=args.gemm)
-    eng.load_state_dict(W)
-    xd, nd = x.to(dev), noise.to(dev)
-    xh, nh = x.pin_memory(), noise.pin_memory()
-    out_h = torch.empty((B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32).pin_memory()
-    gathered = None
-    if world > 1:
-        gathered = torch.empty((world * B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32, device=dev)
-
-    # timing rule: inputs larger than L2, or an explicit flush between iterations.  The default workload's x is 268 MB
-    # per rank; for the small ones (uncertainty: 67 MB, plumbing: 4 MB) a 256 MB buffer is overwritten before every step
-    # INSIDE the timed region (~0.05 ms per step).
-    x_bytes = B * E * wl["h"] * wl["w"] * 4
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if x_bytes < (192 << 20) else None
-
-    def step_device():
-        if flush_buf is not None:
-            flush_buf.zero_()
-        out = eng.sample(xd, nd)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)     # the single gather of final logits
-        return out
-
-    def step_e2e():
-        if flush_buf is not None:
-            flush_buf.zero_()
-        eng.sample_host(xh, nh, out=out_h)                  # H2D x+noise, loop, D2H logits: all inside
-        return out_h
-
-    def timed(fn, steps, sampler=None):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if sampler:
-            sampler.start()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.barrier()
-            ms = float(t.item())
-        return ms, clocks
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    eng.profile(True)
-    ms, clocks = timed(step_device, args.steps, ClockSampler(local) if rank == 0 else None)
-    prof = eng.profile_collect()
-    eng.profile(False)
-    launches = eng.last_launch_count
-    ms_per_step = ms / args.steps
-    value = world * B * args.steps / (ms / 1e3)
-
-    # end to end through the host-buffer entry point
-    step_e2e()
-    t0 = time.perf_counter()
-    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)))
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
-    h2d = (xh.numel() + nh.numel()) * 4
-    d2h = out_h.numel() * 4
-
+    warmup = max(args.warmup, 3)
+    res = measure(args.workload, wl, args, ctx, args.steps, warmup, with_clocks=True)
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    peaks = load_peaks()
-    # dominant kernel class by device time
-    dom = max(prof.items(), key=lambda kv: kv[1][0])
-    dname, (dms, dcount) = dom
-    tokens_per_launch = B * wl["R"] * wl["h"] * wl["w"]
-    fl, by = class_cost(dname, wl)
-    avg_s = dms / max(dcount, 1) / 1e3
-    gemm_like = dname not in ("msda_gather", "step_update", "finalize", "layout")
-    if gemm_like:
-        achieved = fl * tokens_per_launch / avg_s / 1e12
-        roof = {"bound": "tensor", "kernel": dname, "achieved": achieved, "peak": peaks["tensor_sustained"] or peaks["tensor"],
-                "unit": "TFLOP/s", "frac": achieved / (peaks["tensor_sustained"] or peaks["tensor"]),
-                "peak_source": peaks["source"] + " (bf16 dense, sustained)", "traffic": None}
-    else:
-        achieved = by * tokens_per_launch / avg_s / 1e9
-        roof = {"bound": "hbm", "kernel": dname, "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm"], "peak_source": peaks["source"], "traffic": None}
-    # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel class, from the committed capture
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(f"{args.workload}/{args.gemm}", {}).get(dname)
-        if t is not None and wl["per_gpu"] == WORKLOADS[args.workload]["per_gpu"]:
-            roof["traffic"] = t
-    roof["algorithmic_bytes"] = by * tokens_per_launch
-    roof["avg_launch_ms"] = 1e3 * avg_s
-    roof["launches_timed"] = dcount
-    total_prof = sum(v[0] for v in prof.values())
-    roof["share_of_step"] = dms / total_prof if total_prof else None
-    whole = world * B * args.steps * flops_per_image(wl) / (ms / 1e3) / 1e12
-    kernel_ms = {k: round(v[0] / args.steps, 3) for k, v in prof.items() if v[1]}
-
-    # the metric names T=3 as well: same shape, 3 DDIM steps, short run
-    extra = {}
-    if args.workload == "cityscapes_512x1024_T10" and world == 1:
-        eng3 = DecodeEngine(task=wl["task"], num_classes=wl["C"], timesteps=3, accumulation=wl["acc"],
-                            bit_scale=wl["bit_scale"], gemm_mode=args.gemm)
-        eng3.load_state_dict(W)
-        for _ in range(3):
-            eng3.sample(xd, nd)
-        ms3, _ = timed(lambda: eng3.sample(xd, nd), 3)
-        extra["cityscapes_512x1024_T3"] = {"value": B * 3 / (ms3 / 1e3), "unit": "images/s", "ms_per_step": ms3 / 3}
-        del eng3
-
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:        # the CPU leg is reported on rank 0 at N = 1 only
-        cfg = oracle_cfg(wl)
-        cores, thread_log = pick_cpu_threads(cfg, W, x[:1], noise[:1])
-        nsteps = 2 if wl["h"] * wl["w"] >= 16384 else min(wl["T"], 4)
-        t = cpu_reference_step(cfg, W, x[:1], noise[:1], nsteps)
-        cpu_value = 1.0 / (t / nsteps * wl["T"])
-        cpu_baseline = {"value": cpu_value, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"oracle (PyTorch-CPU port pinned to the reference), 1 image, {nsteps} of {wl['T']} "
-                                  f"DDIM steps in {t:.1f} s, scaled to T={wl['T']}; torch threads chosen by timing one step "
-                                  f"each: {thread_log} s of {os.cpu_count()} cores"}
+    # the metric names T = 3 as well, and BASELINE.json lists three more configs: each measured the same way (clean value,
+    # e2e through host buffers, dominant-kernel roofline, GPU and CPU reference legs) with a short run, at N = 1 only
+    also = {}
+    if args.workload == "cityscapes_512x1024_T10" and world == 1 and not args.no_also:
+        for other in ("cityscapes_512x1024_T3", "ade_512x512_T3", "nyu_480x640_T20", "cityscapes_uncertainty_K8_T10"):
+            torch.cuda.empty_cache()
+            also[other] = measure(other, dict(WORKLOADS[other]), args, ctx, 3, 3)
 
     line = {
-        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": "images/sec", "value": res["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else ("f32 via 3xfp16 tensor-core split" if args.gemm == "tc_3xf16" else "f16"),
-        "data": "synthetic", "config": workload_config(wl, args.workload, world * B, args),
-        "clocks": clocks, "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                  "ms_per_step": ms_e2e / e2e_steps},
-        "gpu_launches": launches * args.steps, "launches_per_step": launches,
-        "roofline": roof, "whole_loop_tflops": whole, "kernel_ms_per_step": kernel_ms, "also": extra,
-        "cpu_baseline": cpu_baseline,
+        "data": "synthetic", "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"],
+        "gpu_launches": res["gpu_launches"], "launches_per_step": res["launches_per_step"],
+        "roofline": res["roofline"], "whole_loop_tflops": res["whole_loop_tflops"],
+        "whole_loop_frac_of_tensor_peak": res["whole_loop_frac_of_tensor_peak"],
+        "kernel_ms_per_step": res["kernel_ms_per_step"], "profiled_pass_ms_per_step": res["profiled_pass_ms_per_step"],
+        "gpu_reference": res.get("gpu_reference"), "cpu_baseline": res.get("cpu_baseline"), "also": also,
     }
     print(json.dumps(line), flush=True)
     if dist:

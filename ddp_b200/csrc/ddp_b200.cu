@@ -83,8 +83,20 @@ struct ddp_handle {
     TcWeight tc_in, tc_out;
     TcLayer tcL[kMaxLayers];
     int out_bn = 32;
-    const void* maps_ws = nullptr;      // workspace the activation maps below were encoded for
+    // activation TMA maps of the ACTIVE batch slice (copied from the cache below by ensure_activation_maps)
     CUtensorMap mA_state[2], mA_q[2], mA_g[2], mA_hid[2];
+    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2]; };
+    std::vector<ActMaps> map_cache;     // one entry per (workspace, first image, image count) a call has used since ddp_plan
+    int cur_B = 0, cur_rows = 0;        // images / rows of the slice the launches below work on (== B, rows unless ddp_sample_host chunks)
+
+    // ddp_sample_host pipeline: copy streams + events (created on first use)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> host_ev;
+    int host_chunks = 0;                // DDP_B200_HOST_CHUNKS (0 = automatic)
+    // ddp_sample_host_submit / _wait: two slots, each with its own staging set
+    struct HostSlot { cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr; bool busy = false, used = false; int64_t ticket = 0; };
+    HostSlot slot[2];
+    int64_t next_ticket = 1;
 
     // plan
     int B = 0, R = 0, H = 0, W = 0, N = 0, rows = 0;
@@ -100,6 +112,8 @@ struct ddp_handle {
     std::vector<float> dd_omc, dd_c, dd_std;      // ddpm: (1 - c), c, exp(0.5 log variance) per step
     std::vector<int> dd_noise_on;                 // ddpm: t_next > 0
     const float* step_noise = nullptr;            // ddpm: caller's per-step noise (T, B, R, 256, h, w), device
+    int32_t* unc_changes = nullptr;               // ddp_set_uncertainty_outputs: (B,h,w) device buffers, optional
+    float* unc_spread = nullptr;
     bool sched_override = false, time_dirty = true;
 
     std::vector<Tap> taps;
@@ -501,8 +515,10 @@ struct Workspace {
     float *cond, *state, *q, *V, *samp, *g, *hid, *logits, *accum, *pred;
     uint32_t* rec;          // [rows][N][kRecW] resolved sampling records
     __half *state_hi, *state_lo, *q_hi, *q_lo, *g_hi, *g_lo, *hid_hi, *hid_lo;    // tcgen05 path: fp16 planes
-    float *stage_x, *stage_noise, *stage_out;
+    float *stage_x, *stage_noise, *stage_out;      // host-entry staging, slot 0 (ddp_sample_host, ddp_sample_host_submit)
     int32_t* stage_cls;
+    float *stage2_x, *stage2_noise, *stage2_out;   // slot 1 (ddp_sample_host_submit double buffering)
+    int32_t* stage2_cls;
 };
 
 size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_bytes) {
@@ -540,22 +556,64 @@ size_t carve(const ddp_handle* h, void* base, Workspace* ws, size_t* compute_byt
     w.stage_noise = b.take(rows * cin * N);
     w.stage_out = b.take(B * (c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1) * N);
     w.stage_cls = reinterpret_cast<int32_t*>(b.take(B * N));
+    w.stage2_x = b.take(B * kE * N);
+    w.stage2_noise = b.take(rows * cin * N);
+    w.stage2_out = b.take(B * (c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1) * N);
+    w.stage2_cls = reinterpret_cast<int32_t*>(b.take(B * N));
     if (ws) *ws = w;
     return b.off;
 }
 
-int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& ws) {
-    if (h->maps_ws == ws_base) return DDP_OK;
-    const uint64_t M = (uint64_t)h->rows * h->N;
+// Workspace pointers of the batch slice that starts at image b0 (rows are independent: a slice is a pointer offset).
+Workspace slice_ws(const ddp_handle* h, const Workspace& w, int b0) {
+    if (b0 == 0) return w;
+    const ddp_config& c = h->cfg;
+    const size_t N = h->N, r0 = (size_t)b0 * h->R;
+    const size_t cin = c.task == DDP_TASK_SEG ? kE : 1;
+    const size_t cout = c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 16;
+    const size_t cres = c.task == DDP_TASK_SEG ? (size_t)c.num_classes : 1;
+    Workspace s = w;
+    s.cond += (size_t)b0 * N * kE;
+    s.state += r0 * N * cin;
+    s.q += r0 * N * kE; s.V += r0 * N * kE; s.g += r0 * N * kE;
+    s.samp += r0 * N * kSampW;
+    s.rec += r0 * N * kRecW;
+    if (s.hid) s.hid += r0 * N * kFFN;
+    if (s.state_hi) { s.state_hi += r0 * N * kE; s.state_lo += r0 * N * kE; }
+    if (s.q_hi) { s.q_hi += r0 * N * kE; s.q_lo += r0 * N * kE; s.g_hi += r0 * N * kE; s.g_lo += r0 * N * kE;
+                  s.hid_hi += r0 * N * kFFN; s.hid_lo += r0 * N * kFFN; }
+    s.logits += r0 * N * cout;
+    s.accum += (size_t)b0 * N * cres;
+    s.pred += r0 * N;
+    s.stage_x += (size_t)b0 * kE * N;
+    s.stage_noise += r0 * cin * N;
+    s.stage_out += (size_t)b0 * cres * N;
+    s.stage_cls += (size_t)b0 * N;
+    return s;
+}
+
+// TMA maps of the slice's activation planes; `ws` is ALREADY the slice's view.  Cached per (workspace, b0, nb).
+int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& ws, int b0, int nb) {
+    auto activate = [&](const ddp_handle::ActMaps& a) {
+        memcpy(h->mA_state, a.state, sizeof(a.state)); memcpy(h->mA_q, a.q, sizeof(a.q));
+        memcpy(h->mA_g, a.g, sizeof(a.g)); memcpy(h->mA_hid, a.hid, sizeof(a.hid));
+    };
+    for (const auto& a : h->map_cache)
+        if (a.ws == ws_base && a.b0 == b0 && a.nb == nb) { activate(a); return DDP_OK; }
+    if (h->map_cache.size() >= 16) h->map_cache.erase(h->map_cache.begin());
+    ddp_handle::ActMaps a;
+    a.ws = ws_base; a.b0 = b0; a.nb = nb;
+    const uint64_t M = (uint64_t)nb * h->R * h->N;
     bool ok = true;
     if (h->cfg.task == DDP_TASK_SEG) {
-        ok = ok && tc::make_map_f16(&h->mA_state[0], ws.state_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_state[1], ws.state_lo, M, kE, tc::BM);
+        ok = ok && tc::make_map_f16(&a.state[0], ws.state_hi, M, kE, tc::BM) && tc::make_map_f16(&a.state[1], ws.state_lo, M, kE, tc::BM);
     }
-    ok = ok && tc::make_map_f16(&h->mA_q[0], ws.q_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_q[1], ws.q_lo, M, kE, tc::BM);
-    ok = ok && tc::make_map_f16(&h->mA_g[0], ws.g_hi, M, kE, tc::BM) && tc::make_map_f16(&h->mA_g[1], ws.g_lo, M, kE, tc::BM);
-    ok = ok && tc::make_map_f16(&h->mA_hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&h->mA_hid[1], ws.hid_lo, M, kFFN, tc::BM);
+    ok = ok && tc::make_map_f16(&a.q[0], ws.q_hi, M, kE, tc::BM) && tc::make_map_f16(&a.q[1], ws.q_lo, M, kE, tc::BM);
+    ok = ok && tc::make_map_f16(&a.g[0], ws.g_hi, M, kE, tc::BM) && tc::make_map_f16(&a.g[1], ws.g_lo, M, kE, tc::BM);
+    ok = ok && tc::make_map_f16(&a.hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&a.hid[1], ws.hid_lo, M, kFFN, tc::BM);
     if (!ok) return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation plane");
-    h->maps_ws = ws_base;
+    h->map_cache.push_back(a);
+    activate(a);
     return DDP_OK;
 }
 
@@ -619,6 +677,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* hc = getenv("DDP_B200_HOST_CHUNKS");
+        h->host_chunks = hc ? atoi(hc) : 0;                             // ddp_sample_host pipeline depth (0 = automatic)
         const char* gr = getenv("DDP_B200_GRAPH");
         h->use_graph = gr != nullptr && atoi(gr) != 0;                  // default off
         const char* d = getenv("DDP_B200_FFN_DBG");
@@ -641,6 +701,10 @@ void ddp_destroy(ddp_handle* h) {
     for (auto& r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto& e : h->ev_pool) cudaEventDestroy(e);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    for (auto& e : h->host_ev) cudaEventDestroy(e);
+    for (auto& sl : h->slot) { if (sl.h2d) cudaEventDestroy(sl.h2d); if (sl.done) cudaEventDestroy(sl.done); if (sl.d2h) cudaEventDestroy(sl.d2h); }
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     if (h->w_arena) cudaFree(h->w_arena);
     if (h->tc_arena) cudaFree(h->tc_arena);
     if (h->p_arena) cudaFree(h->p_arena);
@@ -791,6 +855,19 @@ int ddp_set_step_noise(ddp_handle* h, const float* device_noise) {
     return DDP_OK;
 }
 
+int ddp_set_uncertainty_outputs(ddp_handle* h, int32_t* changes, float* spread) {
+    if (!h) return DDP_ERR_INVALID;
+    if (changes && h->cfg.task != DDP_TASK_SEG)
+        return fail(h, DDP_ERR_INVALID, "ddp_set_uncertainty_outputs: class-change counts exist for segmentation only");
+    if (changes != h->unc_changes || spread != h->unc_spread) {
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }      // captured arguments are stale
+        h->graph_warm_key = ddp_handle::GraphKey();
+    }
+    h->unc_changes = changes;
+    h->unc_spread = spread;
+    return DDP_OK;
+}
+
 int ddp_get_schedule(const ddp_handle* h, float* time_in, float* a_now, float* s_now, float* a_next, float* s_next) {
     if (!h) return DDP_ERR_INVALID;
     const int T = h->cfg.timesteps;
@@ -844,7 +921,8 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     int rc = compute_time_constants(h, st);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(st));
-    h->maps_ws = nullptr;
+    h->map_cache.clear();
+    for (auto& sl : h->slot) { sl.busy = false; sl.used = false; }
     h->ws_bytes = carve(h, nullptr, nullptr, &h->ws_compute_bytes);
     if (workspace_bytes) *workspace_bytes = h->ws_bytes;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }      // captured launches are stale
@@ -893,7 +971,7 @@ int64_t ddp_last_launch_count(const ddp_handle* h) {
 static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* film_base, const float* fg_base,
                         const float* fb_base, cudaStream_t st) {
     const ddp_config& c = h->cfg;
-    const int Lc = c.num_layers, N = h->N, M = h->rows * h->N;
+    const int Lc = c.num_layers, N = h->N, M = h->cur_rows * h->N;
     const bool seg = c.task == DDP_TASK_SEG;
     const int C = seg ? c.num_classes : 1;
     const bool s3 = h->nsplit == 3;
@@ -1042,7 +1120,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
 
 static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half* state_hi, __half* state_lo,
                       cudaStream_t st) {
-    const int N = h->N, rows = h->rows;
+    const int N = h->N, rows = h->cur_rows;
     if (h->cfg.task == DDP_TASK_SEG) {
         dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
         KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(src_nchw, state, kE, N)));
@@ -1059,6 +1137,8 @@ static int load_state(ddp_handle* h, const float* src_nchw, float* state, __half
 
 static int sample_impl(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace,
                        size_t workspace_bytes, void* stream);
+static int sample_slice(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace, int b0,
+                        int nb, cudaStream_t st);
 
 // DDP_B200_GRAPH=1: latency mode for small batches (the reference's own use is one image per GPU, where the ~27 launches
 // per DDIM step are a visible fraction of the step).  The first call with a given set of buffers runs normally (kernel
@@ -1152,29 +1232,42 @@ static int sample_impl(ddp_handle* h, const float* x, const float* noise, float*
         return fail(h, DDP_ERR_WORKSPACE, "ddp_sample: workspace %zu < required %zu", workspace_bytes, h->ws_compute_bytes);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return fail(h, DDP_ERR_WORKSPACE, "ddp_sample: workspace must be 256-byte aligned");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    h->launches = 0;
+    return sample_slice(h, x, noise, out, cls, workspace, 0, h->B, static_cast<cudaStream_t>(stream));
+}
+
+// The loop on images [b0, b0 + nb) of the planned batch: x / noise / out / cls point at THAT slice's first image, the
+// workspace is the whole one (the slice's share of every buffer is a pointer offset: rows are independent).  ddp_sample
+// runs one slice = the whole batch; ddp_sample_host pipelines several against the host copies.
+static int sample_slice(ddp_handle* h, const float* x, const float* noise, float* out, int32_t* cls, void* workspace, int b0,
+                        int nb, cudaStream_t st) {
     const ddp_config& c = h->cfg;
-    const int T = c.timesteps, Lc = c.num_layers, N = h->N, rows = h->rows, B = h->B, R = h->R;
+    const int T = c.timesteps, Lc = c.num_layers, N = h->N, R = h->R, B = nb, rows = nb * R;
     const int M = rows * N;                       // tokens in flight
     const bool seg = c.task == DDP_TASK_SEG;
     const int C = seg ? c.num_classes : 1;
-    h->launches = 0;
+    h->cur_B = B; h->cur_rows = rows;
     int rc;
     if (c.diffusion == DDP_DIFFUSION_DDPM && !h->step_noise)
         return fail(h, DDP_ERR_STATE, "ddp_sample: diffusion=ddpm needs ddp_set_step_noise (the reference draws randn_like every step)");
+    if (c.diffusion == DDP_DIFFUSION_DDPM && (b0 != 0 || nb != h->B))
+        return fail(h, DDP_ERR_STATE, "ddp_sample: ddpm runs the whole batch in one slice");
     if (h->time_dirty && (rc = compute_time_constants(h, st))) return rc;
-    Workspace ws;
-    carve(h, workspace, &ws, nullptr);
+    Workspace ws_full, ws;
+    carve(h, workspace, &ws_full, nullptr);
+    ws = slice_ws(h, ws_full, b0);
 
     // cond = W_x x + b: the step-invariant half of transform / down (x is read once, reused for all T steps)
     {
         EpiBias epi{ws.cond, h->b_tr, kE, kE, B * N};
         KLAUNCH(h, DDP_K_COND, st, (launch_gemm_simt<256, true>(x, 0, N, h->Wx_t, kE, B * N, kE, kE, epi, st)));
     }
-    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws))) return rc;
+    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws, b0, nb))) return rc;
     const bool s3 = h->nsplit == 3;
     if ((rc = load_state(h, noise, ws.state, ws.state_hi, ws.state_lo, st))) return rc;
     if (seg) CUDA_TRY(h, cudaMemsetAsync(ws.accum, 0, (size_t)B * N * C * sizeof(float), st));
+    const bool unc = seg && (h->unc_changes || h->unc_spread);
+    if (seg && h->unc_changes) CUDA_TRY(h, cudaMemsetAsync(h->unc_changes + (size_t)b0 * N, 0, (size_t)B * N * sizeof(int32_t), st));
 
     for (int k = 0; k < T; ++k) {
         for (const Override& o : h->overrides)
@@ -1214,6 +1307,9 @@ static int sample_impl(ddp_handle* h, const float* x, const float* noise, float*
             p.ddpm = c.diffusion == DDP_DIFFUSION_DDPM ? 1 : 0;
             p.one_minus_c = h->dd_omc[k]; p.c = h->dd_c[k]; p.std = h->dd_std[k];
             p.step_noise = (p.ddpm && h->dd_noise_on[k]) ? h->step_noise + (size_t)k * M * kE : nullptr;
+            p.row_cls = unc ? reinterpret_cast<uint8_t*>(ws.pred) : nullptr;       // ws.pred is unused by the seg loop otherwise
+            p.changes = h->unc_changes ? h->unc_changes + (size_t)b0 * N : nullptr;
+            p.first_step = k == 0;
             KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
         } else {
             DepthStepParams p;
@@ -1222,6 +1318,7 @@ static int sample_impl(ddp_handle* h, const float* x, const float* noise, float*
             p.conv_bias = h->conv_depth_bias; p.min_depth = c.min_depth; p.max_depth = c.max_depth; p.bit_scale = c.bit_scale;
             p.gamma_now = h->a_now[k]; p.gamma_next = h->a_next[k];
             p.last = last ? 1 : 0;
+            p.spread = h->unc_spread ? h->unc_spread + (size_t)b0 * N : nullptr;
             KLAUNCH(h, DDP_K_STEP, st, (k_depth_step<<<(B * N + 255) / 256, 256, 0, st>>>(p)));
             if ((rc = do_tap(h, DDP_TAP_LOGITS, k, -1, ws.pred, (size_t)M, st))) return rc;
         }
@@ -1230,7 +1327,9 @@ static int sample_impl(ddp_handle* h, const float* x, const float* noise, float*
     if (seg) {
         float count = c.accumulation ? (float)(T * R) : (float)R;
         dim3 grid((N + 31) / 32, (C + 31) / 32, B), block(32, 8);
-        KLAUNCH(h, DDP_K_FINALIZE, st, (k_seg_finalize<<<grid, block, 0, st>>>(ws.accum, out, cls, N, C, count)));
+        KLAUNCH(h, DDP_K_FINALIZE, st, (k_seg_finalize<<<grid, block, 0, st>>>(
+                                           ws.accum, out, cls, N, C, count, reinterpret_cast<const uint8_t*>(ws.pred),
+                                           h->unc_spread ? h->unc_spread + (size_t)b0 * N : nullptr, R)));
     }
     return DDP_OK;
 }
@@ -1284,7 +1383,8 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
     int rc;
     Workspace ws;
     carve(h, workspace, &ws, nullptr);
-    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws))) return rc;
+    h->cur_B = h->B; h->cur_rows = rows;
+    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws, 0, h->B))) return rc;
     // FiLM vectors of the caller's embedding: time_mlp = SiLU -> Linear(1024 -> 512) per layer (transformer.py:275-278, 413-417)
     dim3 g2((2 * kE * 32 + 255) / 256, 1);
     for (int j = 0; j < Lc; ++j) {
@@ -1315,7 +1415,7 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
         p.taps = ws.logits; p.state = ws.state; p.pred = out; p.out = nullptr;
         p.H = h->H; p.W = h->W; p.R = 1; p.B = rows;
         p.conv_bias = h->conv_depth_bias; p.min_depth = c.min_depth; p.max_depth = c.max_depth; p.bit_scale = c.bit_scale;
-        p.gamma_now = 0.5f; p.gamma_next = 0.5f; p.last = 0;
+        p.gamma_now = 0.5f; p.gamma_next = 0.5f; p.last = 0; p.spread = nullptr;
         KLAUNCH(h, DDP_K_STEP, st, (k_depth_step<<<(rows * N + 255) / 256, 256, 0, st>>>(p)));
     }
     return DDP_OK;
@@ -1333,8 +1433,24 @@ int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h
     return DDP_OK;
 }
 
-int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
-                    void* workspace, size_t workspace_bytes, void* stream) {
+// Host buffers in, host buffers out.  The batch is cut into chunks of whole images that flow through a three-stage
+// pipeline: H2D of chunk c+1 (copy stream) under the loop of chunk c (caller's stream), D2H of chunk c's result (second
+// copy stream) under the loop of chunk c+1.  Images are independent (a batched call equals per-image calls bit for bit),
+// so chunking does not change a single bit of the result.  Round 1 ran H2D -> loop -> D2H strictly in series and lost
+// 5 % at N = 1 and 8 % at N = 8 to the un-overlapped PCIe copies ("missing" 8).
+static int host_pipeline_resources(ddp_handle* h, int n_events) {
+    if (!h->h2d_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    if (!h->d2h_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    while ((int)h->host_ev.size() < n_events) {
+        cudaEvent_t e;
+        CUDA_TRY(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->host_ev.push_back(e);
+    }
+    return DDP_OK;
+}
+
+int ddp_sample_host_ex(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                       float* out_device, int chunks, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return DDP_ERR_INVALID;
     if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_sample_host: call ddp_plan first");
     if (!x_host || !noise_host || !out_host || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_sample_host: null pointer");
@@ -1342,23 +1458,142 @@ int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host,
         return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host: workspace %zu < required %zu", workspace_bytes, h->ws_bytes);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
         return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host: workspace must be 256-byte aligned");
+    if (h->slot[0].busy || h->slot[1].busy)
+        return fail(h, DDP_ERR_STATE, "ddp_sample_host: streaming calls are in flight (ddp_sample_host_wait them first)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ddp_config& c = h->cfg;
+    const bool seg = c.task == DDP_TASK_SEG;
+    const size_t N = h->N, R = h->R;
+    const int B = h->B;
+    const size_t cin = seg ? kE : 1, cout = seg ? (size_t)c.num_classes : 1;
+    const size_t x_img = kE * N, n_img = R * cin * N, o_img = cout * N;       // floats per image
+    // chunk count: caller's choice, else DDP_B200_HOST_CHUNKS, else 2 when the inputs are worth overlapping (>= 64 MB) and
+    // every chunk still fills the machine for several waves (>= 2 images of >= 16 k token-rows each); test hooks,
+    // profiling and ddpm run the batch in one piece
+    int nchunk = chunks > 0 ? chunks : h->host_chunks;
+    if (nchunk <= 0) {
+        const size_t in_bytes = (size_t)B * (x_img + n_img) * sizeof(float);
+        nchunk = (in_bytes >= ((size_t)64 << 20) && B >= 4 && (size_t)(B / 2) * R * N >= 32768) ? 2 : 1;
+    }
+    if (!h->taps.empty() || !h->overrides.empty() || h->prof_on || c.diffusion == DDP_DIFFUSION_DDPM) nchunk = 1;
+    if (nchunk > B) nchunk = B;
+    if (nchunk > 8) nchunk = 8;
+    int rc;
+    if ((rc = host_pipeline_resources(h, 2 * nchunk + 1))) return rc;
+    if (h->time_dirty && (rc = compute_time_constants(h, st))) return rc;     // before the copies: it does its own H2D on `st`
+    Workspace ws;
+    carve(h, workspace, &ws, nullptr);
+    float* out_dev = out_device ? out_device : ws.stage_out;
+    cudaEvent_t ev_start = h->host_ev[2 * nchunk];
+    // the staging buffers may still be read by work the caller queued on `st` earlier
+    CUDA_TRY(h, cudaEventRecord(ev_start, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, ev_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, ev_start, 0));
+    int b0s[8], nbs[8];
+    for (int i = 0, b0 = 0; i < nchunk; ++i) {          // contiguous chunks, sizes differ by at most one, the smaller ones first
+        nbs[i] = B / nchunk + (i >= nchunk - B % nchunk ? 1 : 0);
+        b0s[i] = b0;
+        b0 += nbs[i];
+    }
+    for (int i = 0; i < nchunk; ++i) {
+        const size_t b0 = b0s[i], nb = nbs[i];
+        CUDA_TRY(h, cudaMemcpyAsync(ws.stage_x + b0 * x_img, x_host + b0 * x_img, nb * x_img * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(ws.stage_noise + b0 * n_img, noise_host + b0 * n_img, nb * n_img * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaEventRecord(h->host_ev[i], h->h2d_stream));
+    }
+    h->launches = 0;
+    for (int i = 0; i < nchunk; ++i) {
+        const size_t b0 = b0s[i], nb = nbs[i];
+        CUDA_TRY(h, cudaStreamWaitEvent(st, h->host_ev[i], 0));
+        int32_t* cls_dev = (seg && cls_host) ? ws.stage_cls + b0 * N : nullptr;
+        if ((rc = sample_slice(h, ws.stage_x + b0 * x_img, ws.stage_noise + b0 * n_img, out_dev + b0 * o_img, cls_dev, workspace,
+                               (int)b0, (int)nb, st))) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->host_ev[nchunk + i], st));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, h->host_ev[nchunk + i], 0));
+        CUDA_TRY(h, cudaMemcpyAsync(out_host + b0 * o_img, out_dev + b0 * o_img, nb * o_img * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));
+        if (cls_dev)
+            CUDA_TRY(h, cudaMemcpyAsync(cls_host + b0 * N, cls_dev, nb * N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    h->cur_B = h->B; h->cur_rows = h->rows;
+    CUDA_TRY(h, cudaStreamSynchronize(h->d2h_stream));      // the last D2H waits for the last slice, i.e. for everything on `st`
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return DDP_OK;
+}
+
+// Streaming form of the host entry point: up to two calls in flight.  Slot s owns one staging set; its H2D runs on the
+// copy stream as soon as the loop that last read the slot has finished, so the upload of call i+1 and the download of
+// call i-1 hide under the loop of call i — what a serving process with a queue of batches does.
+int ddp_sample_host_submit(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                           float* out_device, void* workspace, size_t workspace_bytes, void* stream, int64_t* ticket) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_sample_host_submit: call ddp_plan first");
+    if (!x_host || !noise_host || !out_host || !workspace || !ticket) return fail(h, DDP_ERR_INVALID, "ddp_sample_host_submit: null pointer");
+    if (workspace_bytes < h->ws_bytes)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host_submit: workspace %zu < required %zu", workspace_bytes, h->ws_bytes);
+    if (reinterpret_cast<uintptr_t>(workspace) % 256)
+        return fail(h, DDP_ERR_WORKSPACE, "ddp_sample_host_submit: workspace must be 256-byte aligned");
+    if (!h->taps.empty() || !h->overrides.empty() || h->prof_on || h->cfg.diffusion == DDP_DIFFUSION_DDPM)
+        return fail(h, DDP_ERR_STATE, "ddp_sample_host_submit: test hooks, profiling and ddpm use the synchronous ddp_sample_host");
+    const int si = !h->slot[0].busy ? 0 : (!h->slot[1].busy ? 1 : -1);
+    if (si < 0) return fail(h, DDP_ERR_STATE, "ddp_sample_host_submit: two calls are already in flight; ddp_sample_host_wait one first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    if ((rc = host_pipeline_resources(h, 1))) return rc;
+    ddp_handle::HostSlot& sl = h->slot[si];
+    if (!sl.h2d) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&sl.h2d, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&sl.d2h, cudaEventDisableTiming));
+    }
+    if (h->time_dirty && (rc = compute_time_constants(h, st))) return rc;
     const ddp_config& c = h->cfg;
     const bool seg = c.task == DDP_TASK_SEG;
     const size_t N = h->N, B = h->B, rows = h->rows;
     const size_t cin = seg ? kE : 1, cout = seg ? (size_t)c.num_classes : 1;
     Workspace ws;
     carve(h, workspace, &ws, nullptr);
-    CUDA_TRY(h, cudaMemcpyAsync(ws.stage_x, x_host, B * kE * N * sizeof(float), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(ws.stage_noise, noise_host, rows * cin * N * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = ddp_sample(h, ws.stage_x, ws.stage_noise, ws.stage_out, (seg && cls_host) ? ws.stage_cls : nullptr, workspace,
-                        workspace_bytes, stream);
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(out_host, ws.stage_out, B * cout * N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (seg && cls_host)
-        CUDA_TRY(h, cudaMemcpyAsync(cls_host, ws.stage_cls, B * N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    float* sx = si ? ws.stage2_x : ws.stage_x;
+    float* sn = si ? ws.stage2_noise : ws.stage_noise;
+    float* so = out_device ? out_device : (si ? ws.stage2_out : ws.stage_out);
+    int32_t* sc = (seg && cls_host) ? (si ? ws.stage2_cls : ws.stage_cls) : nullptr;
+    if (sl.used) {      // the slot's staging was read by an earlier loop / copied out by an earlier D2H: order after them
+        CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, sl.done, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(st, sl.d2h, 0));
+    } else {            // first use: order after whatever the caller queued on `st` before (the workspace may be in use)
+        CUDA_TRY(h, cudaEventRecord(h->host_ev[0], st));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->host_ev[0], 0));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(sx, x_host, B * kE * N * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    CUDA_TRY(h, cudaMemcpyAsync(sn, noise_host, rows * cin * N * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    CUDA_TRY(h, cudaEventRecord(sl.h2d, h->h2d_stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(st, sl.h2d, 0));
+    h->launches = 0;
+    if ((rc = sample_slice(h, sx, sn, so, sc, workspace, 0, (int)B, st))) return rc;
+    CUDA_TRY(h, cudaEventRecord(sl.done, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, sl.done, 0));
+    CUDA_TRY(h, cudaMemcpyAsync(out_host, so, B * cout * N * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));
+    if (sc) CUDA_TRY(h, cudaMemcpyAsync(cls_host, sc, B * N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CUDA_TRY(h, cudaEventRecord(sl.d2h, h->d2h_stream));
+    sl.busy = true; sl.used = true;
+    sl.ticket = h->next_ticket++;
+    *ticket = sl.ticket;
     return DDP_OK;
+}
+
+int ddp_sample_host_wait(ddp_handle* h, int64_t ticket) {
+    if (!h) return DDP_ERR_INVALID;
+    for (auto& sl : h->slot)
+        if (sl.busy && sl.ticket == ticket) {
+            CUDA_TRY(h, cudaEventSynchronize(sl.d2h));
+            sl.busy = false;
+            return DDP_OK;
+        }
+    return fail(h, DDP_ERR_INVALID, "ddp_sample_host_wait: ticket %lld is not in flight", (long long)ticket);
+}
+
+int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    return ddp_sample_host_ex(h, x_host, noise_host, out_host, cls_host, nullptr, 0, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

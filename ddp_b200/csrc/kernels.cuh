@@ -286,6 +286,11 @@ struct SegStepParams {
     int ddpm;
     float one_minus_c, c, std;
     const float* step_noise;   // this step's noise, (rows, 256, h, w) NCHW, or null (t_next == 0: no noise)
+    // per-pixel uncertainty (ddp_set_uncertainty_outputs): class of every (sample, token) at this step, and the running
+    // count of class changes between consecutive steps summed over the R samples
+    uint8_t* row_cls;          // [rows][N] or null
+    int32_t* changes;          // [B][N] or null
+    int first_step;
 };
 
 // One warp per image token (b, n), looping over the R stochastic samples so that the accumulation
@@ -338,6 +343,10 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
                 if (c < C) ac[c] += v[k];
             }
         }
+        if (p.row_cls && lane == 0) {
+            if (p.changes && !p.first_step && p.row_cls[tok] != (uint8_t)besti) p.changes[(size_t)b * p.N + n] += 1;
+            p.row_cls[tok] = (uint8_t)besti;
+        }
         // m <- m_hat * alpha' + ((m - alpha * m_hat) / max(sigma, 1e-8)) * sigma'
         const float* lr = p.lut + (size_t)besti * kE + lane * 8;
         float* st = p.state + tok * kE + lane * 8;
@@ -375,8 +384,10 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
 }
 
 // out[b][c][n] = accum[b][n][c] / count ; cls[b][n] = argmax_c out      (ddp.py:244-245 mean over dim 0)
+// spread[b][n] (optional) = 1 - (#samples r whose LAST-step class equals cls[b][n]) / R      (ddp_set_uncertainty_outputs)
 __global__ void k_seg_finalize(const float* __restrict__ accum, float* __restrict__ out, int32_t* __restrict__ cls,
-                               int N, int C, float count) {
+                               int N, int C, float count, const uint8_t* __restrict__ row_cls = nullptr,
+                               float* __restrict__ spread = nullptr, int R = 1) {
     __shared__ float tile[32][33];
     int b = blockIdx.z;
     int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -391,7 +402,7 @@ __global__ void k_seg_finalize(const float* __restrict__ accum, float* __restric
         int c = c0 + i, n = n0 + threadIdx.x;
         if (n < N && c < C) d[(size_t)c * N + n] = tile[threadIdx.x][i];
     }
-    if (cls != nullptr && blockIdx.y == 0) {
+    if ((cls != nullptr || spread != nullptr) && blockIdx.y == 0) {
         // one thread per token of this tile: argmax over all classes
         int t = threadIdx.y * 32 + threadIdx.x;
         if (t < 32) {
@@ -402,7 +413,12 @@ __global__ void k_seg_finalize(const float* __restrict__ accum, float* __restric
                     float v = __fdiv_rn(s[(size_t)n * C + c], count);
                     if (v > best) { best = v; bi = c; }
                 }
-                cls[(size_t)b * N + n] = bi;
+                if (cls) cls[(size_t)b * N + n] = bi;
+                if (spread) {
+                    int agree = 0;
+                    for (int r = 0; r < R; ++r) agree += row_cls[((size_t)b * R + r) * N + n] == (uint8_t)bi;
+                    spread[(size_t)b * N + n] = __fadd_rn(1.0f, -__fdiv_rn((float)agree, (float)R));
+                }
             }
         }
     }
@@ -444,6 +460,7 @@ struct DepthStepParams {
     float conv_bias, min_depth, max_depth, bit_scale;
     float gamma_now, gamma_next;
     int last;
+    float* spread;         // [B][N] optional: population standard deviation over the R samples of the last-step prediction
 };
 
 // depth head tail + ddim_step.  depth/depth/models/decode_heads/decode_head.py:233-270 (relu(conv3x3)+min_depth),
@@ -482,6 +499,14 @@ __global__ void k_depth_step(DepthStepParams p) {
     if (p.last) {
         float o = __fdiv_rn(sum, (float)p.R);
         p.out[idx] = fminf(fmaxf(o, p.min_depth), p.max_depth);
+        if (p.spread) {
+            float ss = 0.f;
+            for (int r = 0; r < p.R; ++r) {
+                const float e = __fadd_rn(p.pred[((size_t)(b * p.R + r)) * N + n], -o);
+                ss = __fadd_rn(ss, __fmul_rn(e, e));
+            }
+            p.spread[idx] = sqrtf(__fdiv_rn(ss, (float)p.R));
+        }
     }
 }
 

@@ -140,10 +140,13 @@ class DecodeEngine:
 
     # ------------------------------------------------------------------ the hot path
     def sample(self, x: torch.Tensor, noise: torch.Tensor, return_cls=False, step_noise: Optional[torch.Tensor] = None,
-               out: Optional[torch.Tensor] = None):
+               out: Optional[torch.Tensor] = None, return_uncertainty=False):
         """x (B,256,h,w), noise (B,R,Cin,h,w): CUDA fp32 tensors -> out (B,C,h,w) [, cls (B,h,w) int32].
         diffusion='ddpm' also needs step_noise (T,B,R,256,h,w): what the reference draws with randn_like every step.
         `out`: optional preallocated result buffer (stable addresses are what the DDP_B200_GRAPH=1 latency mode keys on).
+
+        return_uncertainty: also return {"changes": (B,h,w) int32 (seg), "spread": (B,h,w) fp32} — per-pixel class-change
+        counts over steps and samples, and the disagreement of the R samples at the last step (include/ddp_b200.h).
 
         Asynchronous on torch's current stream."""
         if self.diffusion == "ddpm":
@@ -169,12 +172,22 @@ class DecodeEngine:
         elif tuple(out.shape) != (B, self.num_classes, h, w) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous CUDA fp32 tensor of shape {(B, self.num_classes, h, w)}")
         cls = torch.empty((B, h, w), dtype=torch.int32, device=x.device) if (return_cls and self.task == "seg") else None
+        unc = None
+        if return_uncertainty:
+            unc = {"spread": torch.empty((B, h, w), dtype=torch.float32, device=x.device)}
+            if self.task == "seg":
+                unc["changes"] = torch.empty((B, h, w), dtype=torch.int32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_set_uncertainty_outputs(
+                self._h, unc["changes"].data_ptr() if unc and "changes" in unc else None, unc["spread"].data_ptr() if unc else None))
             self._check(self.lib.ddp_sample(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
                                             cls.data_ptr() if cls is not None else None,
                                             self._ws_ptr(), self._ws_bytes, stream))
-        return (out, cls) if return_cls else out
+        res = (out, cls) if return_cls else out
+        if return_uncertainty:
+            return (res + (unc,)) if return_cls else (res, unc)
+        return res
 
     def head_forward(self, feat: torch.Tensor, time_embedding: torch.Tensor):
         """One denoiser call: feat (rows,256,h,w) CUDA fp32, time_embedding (1024,) -> (rows,C,h,w) logits / depth.
@@ -207,8 +220,10 @@ class DecodeEngine:
         return cls
 
     def sample_host(self, x: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None,
-                    cls: Optional[torch.Tensor] = None):
-        """Host tensors in (ideally pinned), host tensors out; the copies are part of the call."""
+                    cls: Optional[torch.Tensor] = None, out_device: Optional[torch.Tensor] = None, chunks: int = 0):
+        """Host tensors in (ideally pinned), host tensors out; the copies are part of the call and are pipelined against
+        the loop in `chunks` groups of images (0 = automatic).  `out_device`: optional CUDA (B,C,h,w) tensor that also
+        receives the result (the send buffer of the NCCL gather)."""
         B, c, h, w = x.shape
         R = noise.shape[1]
         assert not x.is_cuda and not noise.is_cuda
@@ -217,12 +232,39 @@ class DecodeEngine:
         self.plan(B, R, h, w)
         if out is None:
             out = torch.empty((B, self.num_classes, h, w), dtype=torch.float32).pin_memory()
+        if out_device is not None:
+            self._on_device(out_device)
+            assert tuple(out_device.shape) == (B, self.num_classes, h, w) and out_device.dtype == torch.float32 and out_device.is_contiguous()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
-            self._check(self.lib.ddp_sample_host(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
-                                                 cls.data_ptr() if cls is not None else None,
-                                                 self._ws_ptr(), self._ws_bytes, stream))
+            self._check(self.lib.ddp_sample_host_ex(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                                                    cls.data_ptr() if cls is not None else None,
+                                                    out_device.data_ptr() if out_device is not None else None, int(chunks),
+                                                    self._ws_ptr(), self._ws_bytes, stream))
         return out
+
+    def submit_host(self, x: torch.Tensor, noise: torch.Tensor, out: torch.Tensor, cls: Optional[torch.Tensor] = None,
+                    out_device: Optional[torch.Tensor] = None) -> int:
+        """Streaming form of sample_host: returns a ticket at once, at most two calls in flight; wait_host(ticket) blocks
+        until `out` (pinned host tensor) is complete.  The upload of the next call overlaps this call's loop."""
+        B, c, h, w = x.shape
+        R = noise.shape[1]
+        assert not x.is_cuda and not noise.is_cuda and x.is_contiguous() and noise.is_contiguous()
+        assert not out.is_cuda and tuple(out.shape) == (B, self.num_classes, h, w) and out.is_contiguous()
+        self.plan(B, R, h, w)
+        if out_device is not None:
+            self._on_device(out_device)
+        ticket = ctypes.c_int64()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_sample_host_submit(self._h, x.data_ptr(), noise.data_ptr(), out.data_ptr(),
+                                                        cls.data_ptr() if cls is not None else None,
+                                                        out_device.data_ptr() if out_device is not None else None,
+                                                        self._ws_ptr(), self._ws_bytes, stream, ctypes.byref(ticket)))
+        return ticket.value
+
+    def wait_host(self, ticket: int):
+        self._check(self.lib.ddp_sample_host_wait(self._h, ticket))
 
     @property
     def last_launch_count(self):

@@ -131,6 +131,16 @@ int ddp_set_schedule(ddp_handle* h, int timesteps, const float* time_in, const f
 int ddp_set_ddpm_schedule(ddp_handle* h, int timesteps, const float* one_minus_c, const float* c, const float* std_dev,
                           const int32_t* noise_on);
 int ddp_set_step_noise(ddp_handle* h, const float* device_noise);
+/* Per-pixel uncertainty maps (README "uncertainty awareness").  The reference exposes its stochastic
+ * samples only through randsteps + the mean (ddp.py:219, 245); these two optional extra outputs of the following
+ * ddp_sample / ddp_sample_host calls are DEFINED here and pinned by oracle/ddp_oracle.py::uncertainty:
+ *   changes (B,h,w) int32, seg only: sum over the R samples of the number of steps k >= 1 whose argmax class differs
+ *                                    from the same sample's class at step k-1;
+ *   spread  (B,h,w) fp32: seg   1 - (number of samples whose LAST-step class equals the returned map's class) / R,
+ *                         depth the population standard deviation over the R samples of the last-step prediction.
+ * Device pointers, caller-owned, either may be NULL; they stay registered until changed.  Cost: one byte per (sample,
+ * token) and step inside the existing step kernel — no extra launch. */
+int ddp_set_uncertainty_outputs(ddp_handle* h, int32_t* changes, float* spread);
 /* Read back the schedule in use (after ddp_plan). */
 int ddp_get_schedule(const ddp_handle* h, float* time_in, float* a_now, float* s_now,
                      float* a_next, float* s_next);
@@ -169,6 +179,24 @@ int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h
  * for staging (ddp_plan's size already includes it). */
 int ddp_sample_host(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host,
                     int32_t* cls_host, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with two more arguments.  `chunks`: the batch is cut into that many contiguous groups of whole images which are
+ * pipelined (H2D of group c+1 and D2H of group c-1 on two copy streams under the loop of group c on `stream`); 0 = automatic
+ * (environment DDP_B200_HOST_CHUNKS, else 2 for inputs >= 64 MB, else 1).  Images are independent, so the result does not
+ * depend on `chunks`.  `out_device`: optional (B,C,h,w) device buffer that also receives the result — e.g. the send
+ * buffer of the one NCCL gather — instead of the workspace's staging area.  Pinned host memory is needed for
+ * the copies to overlap; pageable memory works but serialises. */
+int ddp_sample_host_ex(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                       float* out_device, int chunks, void* workspace, size_t workspace_bytes, void* stream);
+/* Streaming form for a queue of batches (a serving process, an evaluation loop over a dataset — the reference's
+ * single_gpu_test / multi_gpu_test loops, segmentation/mmseg/apis/test.py:91, 208): submit returns at once with a ticket,
+ * at most TWO calls may be in flight (two staging sets inside the workspace); the upload of call i+1 and the download of
+ * call i-1 run on copy streams under the loop of call i.  ddp_sample_host_wait blocks until that call's out_host (and
+ * cls_host) are complete.  x_host / noise_host must stay valid and unchanged until the NEXT submit on the same handle has
+ * been waited for or this call's wait returned, out_host until this call's wait returned.  Results are bit-identical to
+ * ddp_sample_host.  Pinned host memory required for the overlap. */
+int ddp_sample_host_submit(ddp_handle* h, const float* x_host, const float* noise_host, float* out_host, int32_t* cls_host,
+                           float* out_device, void* workspace, size_t workspace_bytes, void* stream, int64_t* ticket);
+int ddp_sample_host_wait(ddp_handle* h, int64_t ticket);
 
 /* Test hooks.  A tap copies one intermediate of (step, layer) into caller-owned device memory during
  * the next ddp_sample calls; ddp_set_state_override makes step `step` start from the given state

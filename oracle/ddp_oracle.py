@@ -35,6 +35,7 @@ Reference file:line followed by each function (paths relative to
   head_depth            depth/depth/models/decode_heads/deformable_head_with_time.py:89-131,
                         depth/depth/models/decode_heads/decode_head.py:100,233-270
   sample_depth          depth/depth/models/depther/ddp.py:220-247, 97-110
+  uncertainty           (no reference counterpart: defined here on the loop's per-step class maps, ddp.py:219,235,245)
 
 Batched generalisation: the reference loop only works for one image (its
 batch dimension is ``randsteps``); here rows are (image b, sample r) with
@@ -485,6 +486,27 @@ def sample(W, cfg: OracleConfig, x, noise, trace: bool = False, ddpm_noise=None)
     if cfg.task == "seg":
         return ddim_sample_seg(W, cfg, x, noise, trace, ddpm_noise)
     return sample_depth(W, cfg, x, noise, trace)
+
+
+def uncertainty(W, cfg: OracleConfig, x, noise):
+    """Per-pixel uncertainty maps of the library (ddp_set_uncertainty_outputs).  The reference has no such output: it
+    exposes its stochastic samples only as ``randsteps`` + the mean (segmentation/mmseg/models/segmentors/ddp.py:219, 245;
+    README abstract "uncertainty awareness"), so the definitions are made here, on the reference loop's own per-step
+    class maps, and the CUDA path is checked against them:
+      seg   changes (B,h,w) int32 = sum over samples r and steps k >= 1 of [argmax_k != argmax_{k-1}]
+            spread  (B,h,w)       = 1 - mean_r [argmax of sample r at the LAST step == argmax of the returned map]
+      depth spread  (B,h,w)       = population standard deviation over r of the last-step prediction
+    -> (out, changes or None, spread)."""
+    out, traces = sample(W, cfg, x, noise, trace=True)
+    changes, spread = [], []
+    for b, tr in enumerate(traces):
+        if cfg.task == "seg":
+            am = torch.stack(tr.argmax)                                   # (T,R,h,w)
+            changes.append((am[1:] != am[:-1]).sum((0, 1)).to(torch.int32))
+            spread.append(1.0 - (am[-1] == out[b].argmax(0)[None]).float().mean(0))
+        else:
+            spread.append(tr.logits[-1][:, 0].std(0, unbiased=False))
+    return out, (torch.stack(changes) if changes else None), torch.stack(spread)
 
 
 def make_inputs(cfg: OracleConfig, B, h, w, seed=1234, dtype=torch.float32):

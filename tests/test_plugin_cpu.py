@@ -241,7 +241,11 @@ def _gloo_worker(rank, world, port, batch, q):
         def fake_sample(xl, nl):                 # stands in for engine.sample on this rank's shard
             return xl * 2 + nl.mean(1)
         out = D.distributed_sample(fake_sample, x, noise)
-        q.put((rank, torch.equal(out, x * 2 + noise.mean(1)), tuple(out.shape)))
+        ok = torch.equal(out, x * 2 + noise.mean(1))
+        # the small-payload form: a per-rank post step (stands in for engine.resize_argmax) and ONE gather of uint8 class maps
+        cls = D.distributed_sample(fake_sample, x, noise, post=lambda lg: lg.argmax(1).to(torch.uint8))
+        ok = ok and cls.dtype == torch.uint8 and torch.equal(cls, (x * 2 + noise.mean(1)).argmax(1).to(torch.uint8))
+        q.put((rank, ok, tuple(out.shape)))
     finally:
         dist.destroy_process_group()
 
