@@ -402,6 +402,12 @@ struct EpiParams {
     // EPI_RES_LN: y = LN(acc*scale + bias) * g + b; the residual is part of the accumulator (identity block of W),
     // g / b already carry the FiLM (scale+1), shift
     const float* ln_g; const float* ln_b;
+    // 3x3 convolution as an implicit GEMM (the neck, fpn.py:130-139): the A planes hold a ZERO-BORDERED token grid
+    // [imgs][(H + 2) * (W + 2)][256] with row pitch conv_pitch = W + 2, K = 9 * 256 with k = tap * 256 + c.  K block kb
+    // (tap = kb / 4) loads the A tile shifted by (tap / 3 - 1) rows and (tap % 3 - 1) columns = a plain offset of the TMA row
+    // coordinate: the zero border supplies the padding and keeps shifts from wrapping into the neighbouring row / image,
+    // rows outside the tensor are zero-filled by TMA.  0 = ordinary GEMM.
+    int conv_pitch;
 };
 
 // Sampling-projection epilogue of ONE warp.  Accumulator columns at t_row: 0..63 = (x, y) offsets of 32 sampling points
@@ -568,11 +574,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     uint8_t* st = smem + stage * C::kStageBytes;
                     if (leader) mbar_expect_tx(&full_bar[stage], kNCta * C::kStageBytes);   // bytes of both CTAs land on the leader's barrier
                     const bool second = kb >= n_kb1;
-                    const int ka = (second ? kb - n_kb1 : kb) * BK;
-                    load(st, second ? &mapA2hi : &mapAhi, &full_bar[stage], ka, m0);
+                    int ka = (second ? kb - n_kb1 : kb) * BK;
+                    int ma = m0;
+                    if (ep.conv_pitch) {                       // implicit 3x3 convolution: tap-shifted rows of the bordered grid
+                        const int tap = kb / (kE / BK);
+                        ka = (kb - tap * (kE / BK)) * BK;
+                        ma = m0 + (tap / 3 - 1) * ep.conv_pitch + (tap % 3 - 1);
+                    }
+                    load(st, second ? &mapA2hi : &mapAhi, &full_bar[stage], ka, ma);
                     load(st + C::kABytes, &mapBhi, &full_bar[stage], kb * BK, n0);
                     if (NSPLIT > 1) {
-                        load(st + C::kABytes + C::kBBytes, second ? &mapA2lo : &mapAlo, &full_bar[stage], ka, m0);
+                        load(st + C::kABytes + C::kBBytes, second ? &mapA2lo : &mapAlo, &full_bar[stage], ka, ma);
                         load(st + 2 * C::kABytes + C::kBBytes, &mapBlo, &full_bar[stage], kb * BK, n0);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -603,6 +615,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                     const uint64_t b_hi = make_smem_desc(st + C::kABytes);
                     const uint64_t a_lo = make_smem_desc(st + C::kABytes + C::kBBytes);
                     const uint64_t b_lo = make_smem_desc(st + 2 * C::kABytes + C::kBBytes);
+                    // K blocks past K1 multiply the residual operand by the 2^shift * I block of the augmented weight: a power
+                    // of two is exact in fp16, its lo plane is all zeros, so the a_hi * b_lo MMA adds exactly nothing
+                    const bool ident = EPI == EPI_RES_LN && kb >= n_kb1;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);       // +32 B per K=16 step inside the swizzle atom
@@ -610,7 +625,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         if (elect_one()) {
                             if (NSPLIT > 1) {
                                 umma(d_tmem, a_lo + koff, b_hi + koff, accum);    // small terms first
-                                umma(d_tmem, a_hi + koff, b_lo + koff, 1u);
+                                if (!ident) umma(d_tmem, a_hi + koff, b_lo + koff, 1u);
                                 umma(d_tmem, a_hi + koff, b_hi + koff, 1u);
                             } else {
                                 umma(d_tmem, a_hi + koff, b_hi + koff, accum);

@@ -28,9 +28,90 @@ __global__ void __launch_bounds__(256) k_for_each(F f, size_t n) {
     if (idx < n) f(idx);
 }
 
+// ---- tensor-core path of the 3x3 convolutions (85 % of the neck's FLOPs): tc_3xf16 arithmetic of the decode loop ----
+// The convolution is an implicit GEMM of the loop's tcgen05 kernel (gemm_tc.cuh, EpiParams::conv_pitch): the normalised
+// level map is written once as fp16 hi/lo planes on a ZERO-BORDERED token grid [(H + 2) * (W + 2)], every (tap, 64-channel)
+// K block is one TMA box load of the same planes at a shifted row coordinate (no im2col buffer), the accumulator lives in
+// TMEM, and the bordered fp32 result is compacted back to the token-major map the GroupNorm kernels read.
+struct PadSplit {            // idx = bordered token * 32 + 8-channel group
+    const float* src; __half* hi; __half* lo; int H, W;
+    __device__ __forceinline__ void operator()(size_t idx) const {
+        const int c8 = (int)(idx & 31);
+        const size_t t = idx >> 5;
+        const int Wp = W + 2, Np = (H + 2) * Wp;
+        const size_t b = t / Np;
+        const int n = (int)(t - b * Np);
+        const int ip = n / Wp, jp = n - ip * Wp;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ip >= 1 && ip <= H && jp >= 1 && jp <= W) {
+            const float* sp = src + ((b * H + (ip - 1)) * (size_t)W + (jp - 1)) * kC + c8 * 8;
+            const float4 a = *reinterpret_cast<const float4*>(sp), c = *reinterpret_cast<const float4*>(sp + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+        }
+        split8_store(v, hi + t * kC + c8 * 8, lo + t * kC + c8 * 8);
+    }
+};
+struct Unpad {               // idx = token * 64 + float4 group
+    const float* src; float* dst; int H, W;
+    __device__ __forceinline__ void operator()(size_t idx) const {
+        const int c4 = (int)(idx & 63);
+        const size_t t = idx >> 6;
+        const int N = H * W, Wp = W + 2;
+        const size_t b = t / N;
+        const int n = (int)(t - b * N);
+        const int i = n / W, j = n - i * W;
+        const size_t tp = b * (size_t)(H + 2) * Wp + (size_t)(i + 1) * Wp + (j + 1);
+        *reinterpret_cast<float4*>(dst + t * kC + c4 * 4) = *reinterpret_cast<const float4*>(src + tp * kC + c4 * 4);
+    }
+};
+
+// GroupNorm statistics, second stage: one WARP per (image, group) instead of one thread (the one-thread form walked
+// 512 chunks x 8 channels of fp64 partials serially: 0.45 ms per launch, 21 % of the neck, for 256 threads of work).
+__global__ void __launch_bounds__(256) k_gn_finalize_warp(GnFinalize f, size_t n) {
+    const size_t idx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (idx >= n) return;
+    const int g = (int)(idx % f.G);
+    const size_t b = idx / f.G;
+    const int cpg = f.C / f.G;
+    double s = 0.0, ss = 0.0;
+    for (int e = lane; e < f.chunks * cpg; e += 32) {
+        const int chunk = e / cpg, k = e - chunk * cpg;
+        const size_t p = ((b * f.chunks + chunk) * f.C + (size_t)g * cpg + k) * 2;
+        s += f.part[p];
+        ss += f.part[p + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+        const double cnt = (double)f.N * cpg;
+        const double mean = s / cnt;
+        double var = ss / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        f.stats[idx * 2] = (float)mean;
+        f.stats[idx * 2 + 1] = (float)(1.0 / sqrt(var + (double)f.eps));
+    }
+}
+
+struct NeckTc {
+    bool on = false;
+    int num_sms = 148;
+    __half* w_arena = nullptr;                      // per level: hi [256][9 * 256], lo [256][9 * 256], k = tap * 256 + ci
+    CUtensorMap w_hi[kMaxLevels], w_lo[kMaxLevels];
+    float inv_scale[kMaxLevels] = {1.f, 1.f, 1.f, 1.f};
+};
+
 struct CudaBackend {
     cudaStream_t st;
+    const NeckTc* tc = nullptr;
+    const Weights* w = nullptr;
+    const Dims* d = nullptr;
+    char* conv_scratch = nullptr;
     int64_t launches = 0;
+    cudaError_t err = cudaSuccess;
 
     template <class F>
     void for_each(size_t n, const F& f) {
@@ -38,7 +119,38 @@ struct CudaBackend {
         k_for_each<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n);
         ++launches;
     }
+    void for_each(size_t n, const GnFinalize& f) {          // overload: one warp per (image, group)
+        if (n == 0) return;
+        k_gn_finalize_warp<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(f, n);
+        ++launches;
+    }
+    // 3x3 convolution of level l on the tensor cores; false = not available for this call (fp32 path takes over)
+    bool conv3_tc(const float* A, const float* Wt, float* out) {
+        if (!tc || !tc->on || !conv_scratch) return false;
+        int l = -1;
+        for (int i = 0; i < d->L; ++i) if (w->fpn_t[i] == Wt) l = i;
+        if (l < 0) return false;
+        const int H = d->H[l], W = d->W[l];
+        const size_t Mp = (size_t)d->B * (H + 2) * (W + 2);
+        if (Mp >= (1ull << 31) / 2) return false;
+        __half* hi = reinterpret_cast<__half*>(conv_scratch);
+        __half* lo = hi + Mp * kC;
+        float* out_pad = reinterpret_cast<float*>(lo + Mp * kC);
+        CUtensorMap a_hi, a_lo;
+        if (!ddp::tc::make_map_f16(&a_hi, hi, Mp, kC, ddp::tc::BM) || !ddp::tc::make_map_f16(&a_lo, lo, Mp, kC, ddp::tc::BM)) return false;
+        for_each(Mp * 32, PadSplit{A, hi, lo, H, W});
+        ddp::tc::EpiParams ep{};
+        ep.scale = tc->inv_scale[l]; ep.bias = nullptr; ep.out = out_pad; ep.ldc = kC; ep.ncols = kC;
+        ep.conv_pitch = W + 2;
+        cudaError_t e = ddp::tc::launch_gemm_tc<256, 3, ddp::tc::EPI_BIAS>(a_hi, a_lo, a_hi, a_lo, tc->w_hi[l], tc->w_lo[l], (int)Mp,
+                                                                         9 * kC, 9 * kC, kC, ep, tc->num_sms, st);
+        if (e != cudaSuccess) { err = e; return false; }
+        ++launches;
+        for_each((size_t)d->B * H * W * 64, Unpad{out_pad, out, H, W});
+        return true;
+    }
     void gemm(int mode, const float* A, int lda, int n_img, const float* Wt, long long M, int K, float* out) {
+        if (mode == A_CONV3 && conv3_tc(A, Wt, out)) return;
         EpiBias epi{out, nullptr, kC, kC, (int)M};
         if (mode == A_ROW_MAJOR) launch_gemm_simt<256, A_ROW_MAJOR>(A, lda, n_img, Wt, kC, (int)M, K, kC, epi, st);
         else if (mode == A_NCHW) launch_gemm_simt<256, A_NCHW>(A, lda, n_img, Wt, kC, (int)M, K, kC, epi, st);
@@ -66,6 +178,7 @@ struct ddp_neck {
     float* w_arena = nullptr;
     ddp::neck::Weights w{};
     ddp::neck::Dims dims{};
+    ddp::neck::NeckTc tc;        // tensor-core 3x3 convolutions (DDP_B200_NECK_TC, default on)
     size_t ws_bytes = 0;
     int64_t launches = 0;
 };
@@ -143,6 +256,12 @@ int ddp_neck_create(const ddp_neck_config* cfg, ddp_neck** out) {
     ddp_neck* h = new ddp_neck();
     h->cfg = *cfg;
     h->device = dev;
+    {
+        const char* e = getenv("DDP_B200_NECK_TC");                    // 0 = fp32 CUDA-core 3x3 convolutions (the first path)
+        h->tc.on = (e == nullptr || atoi(e) != 0) && ddp::tc::get_encode_fn() != nullptr;
+        int sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) h->tc.num_sms = sms;
+    }
     const int L = cfg->num_levels;
     auto add = [&](const std::string& name, int64_t numel) {
         ddp_neck::Spec s;
@@ -174,6 +293,7 @@ int ddp_neck_create(const ddp_neck_config* cfg, ddp_neck** out) {
 }
 
 void ddp_neck_destroy(ddp_neck* h) {
+    if (h && h->tc.w_arena) cudaFree(h->tc.w_arena);
     if (!h) return;
     if (h->w_arena) cudaFree(h->w_arena);
     delete h;
@@ -249,6 +369,40 @@ int ddp_neck_commit_weights(ddp_neck* h) {
         w.down_b = h->w_arena + offs[i++];
     }
     h->w = w;
+    if (h->tc.on && (h->cfg.stages & STAGE_FPN)) {
+        // 3x3 weights as fp16 hi/lo planes [256 out][k = tap * 256 + ci] of 2^shift * W (shift per level: the largest
+        // |w| lands in [128, 256), so both planes are normal fp16 numbers), split on the host, one upload
+        const size_t per = (size_t)kC * 9 * kC;
+        std::vector<__half> planes(2 * per * L);
+        for (int l = 0; l < L; ++l) {
+            const std::vector<float>& src = neck_host(h, "fpn_convs." + std::to_string(l) + ".conv.weight");   // (256,256,3,3)
+            float mx = 0.f;
+            for (float v : src) mx = fmaxf(mx, fabsf(v));
+            int e = 0, shift = 0;
+            if (mx > 0.f && isfinite(mx)) { frexpf(mx, &e); shift = 8 - e; shift = shift > 15 ? 15 : (shift < -8 ? -8 : shift); }
+            const float scale = ldexpf(1.0f, shift);
+            h->tc.inv_scale[l] = 1.0f / (scale * ddp::tc::kActScale);
+            __half* hi = planes.data() + (size_t)l * 2 * per;
+            __half* lo = hi + per;
+            for (int co = 0; co < kC; ++co)
+                for (int ci = 0; ci < kC; ++ci)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const float sv = src[((size_t)co * kC + ci) * 9 + tap] * scale;
+                        const __half hh = __float2half_rn(sv);
+                        const size_t k = (size_t)co * 9 * kC + (size_t)tap * kC + ci;
+                        hi[k] = hh;
+                        lo[k] = __float2half_rn(sv - __half2float(hh));
+                    }
+        }
+        if (h->tc.w_arena) { cudaFree(h->tc.w_arena); h->tc.w_arena = nullptr; }
+        NECK_CUDA_TRY(h, cudaMalloc(&h->tc.w_arena, planes.size() * sizeof(__half)));
+        NECK_CUDA_TRY(h, cudaMemcpy(h->tc.w_arena, planes.data(), planes.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        for (int l = 0; l < L; ++l) {
+            __half* hi = h->tc.w_arena + (size_t)l * 2 * per;
+            if (!ddp::tc::make_map_f16(&h->tc.w_hi[l], hi, kC, 9 * kC, 256) || !ddp::tc::make_map_f16(&h->tc.w_lo[l], hi + per, kC, 9 * kC, 256))
+                return nfail(h, DDP_ERR_CUDA, "ddp_neck_commit_weights: cuTensorMapEncodeTiled failed for the 3x3 weight planes of level %d", l);
+        }
+    }
     h->committed = true;
     return DDP_OK;
 }
@@ -300,8 +454,10 @@ int ddp_neck_forward(ddp_neck* h, const float* const* inputs, float* x_out, floa
     Buffers buf;
     carve(d, static_cast<char*>(workspace), &buf);
     CudaBackend be{static_cast<cudaStream_t>(stream)};
+    be.tc = &h->tc; be.w = &h->w; be.d = &h->dims; be.conv_scratch = buf.conv_scratch;
     neck_run(be, d, h->w, buf, inputs, x_out, fpn_outs);
     h->launches = be.launches;
+    NECK_CUDA_TRY(h, be.err);
     NECK_CUDA_TRY(h, cudaGetLastError());
     return DDP_OK;
 }

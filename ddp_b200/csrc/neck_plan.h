@@ -202,7 +202,19 @@ struct Buffers {
     float* z[kMaxLevels];    // [B][N_l][256] per-level slices of the `down` conv
     double* part;            // GroupNorm partial sums
     float* stats;            // [B][groups][2]
+    char* conv_scratch;      // tensor-core 3x3 convolution (CUDA build): zero-bordered fp16 planes + bordered fp32 output
 };
+
+// bytes of the bordered-grid scratch of the tensor-core 3x3 convolution at the largest level: per bordered token
+// (H + 2) * (W + 2): 256 channels x (fp16 hi + fp16 lo + fp32 out)
+inline size_t conv_scratch_bytes(const Dims& d) {
+    size_t mx = 0;
+    for (int l = 0; l < d.L; ++l) {
+        const size_t mp = (size_t)d.B * (d.H[l] + 2) * (d.W[l] + 2);
+        mx = mp > mx ? mp : mx;
+    }
+    return mx * kC * 8 + 1024;
+}
 
 inline size_t gn_chunks(long long N) { return (size_t)((N + kGnChunk - 1) / kGnChunk); }
 
@@ -225,6 +237,7 @@ inline size_t carve(const Dims& d, char* base, Buffers* out) {
     for (int l = 0; l < d.L; ++l) max_tokens = d.tokens(l) > max_tokens ? d.tokens(l) : max_tokens;
     b.part = reinterpret_cast<double*>(take((size_t)d.B * gn_chunks(max_tokens) * kC * 2 * sizeof(double)));
     b.stats = reinterpret_cast<float*>(take((size_t)d.B * d.groups * 2 * sizeof(float)));
+    b.conv_scratch = (d.stages & STAGE_FPN) ? take(conv_scratch_bytes(d)) : nullptr;
     if (out) *out = b;
     return off;
 }

@@ -1,10 +1,9 @@
 """GPU parity tests of the neck (FPN + MultiStageMerging) through the C ABI: against the golden outputs
 of the unmodified reference modules and against the oracle.
 
-STATUS: this row was built after the round-1 GPU budget was spent.  Its launch sequence and kernel bodies are checked
-against the oracle by the host emulation (tests/test_neck_emu_cpu.py); the CUDA build itself has not run on hardware
-yet, hence `first_hw_run` (collected last, non-strict xfail — see tests/conftest.py).  Remove the marker after the
-first green GPU run.
+Round 2: all of these run green on a B200 (the round-1 hardware failures were one Python line in NeckEngine.weight_names,
+profiles/r02_hw/).  The 3x3 convolutions run on the tensor cores by default (tc_3xf16 implicit GEMM, DDP_B200_NECK_TC=1);
+`test_neck_fp32_conv_path_still_correct` keeps the fp32 CUDA-core path covered.
 """
 import os
 
@@ -38,7 +37,18 @@ def test_neck_matches_reference_golden(path):
         assert d < TOL, f"fpn level {l}: max|d| = {d:.3e}"
     d = (x.cpu() - torch.from_numpy(g["out"])).abs().max().item()
     assert d < TOL, f"x: max|d| = {d:.3e}"
-    assert eng.last_launch_count == 4 + 4 * 3 + 4 * (1 + 3 + 1) + 4 + 1 + 3 + 1
+    conv = 3 if os.environ.get("DDP_B200_NECK_TC", "1") != "0" else 1      # tensor-core conv: border+split, implicit GEMM, compaction
+    assert eng.last_launch_count == 4 + 4 * 3 + 4 * (conv + 3 + 1) + 4 + 1 + 3 + 1
+
+
+def test_neck_fp32_conv_path_still_correct(monkeypatch):
+    """DDP_B200_NECK_TC=0: the 3x3 convolutions on the fp32 CUDA-core GEMM (tile loader with shifted tokens)."""
+    monkeypatch.setenv("DDP_B200_NECK_TC", "0")
+    W, xs, g = load_neck_case(golden_files("neck")[0])
+    eng = make_engine(W, [x.shape[1] for x in xs])
+    x, _ = eng.forward([t.cuda() for t in xs])
+    assert (x.cpu() - torch.from_numpy(g["out"])).abs().max().item() < TOL
+    assert eng.last_launch_count == 4 + 4 * 3 + 4 * (1 + 3) + 4 + 1 + 3 + 1
 
 
 @pytest.mark.parametrize("B,h,w", [(1, 1, 1), (2, 5, 3), (1, 9, 17), (3, 4, 4), (2, 33, 65)])
@@ -121,10 +131,10 @@ def test_plugin_fused_neck_feeds_the_decode_loop():
     want_x = NO.neck(Wn, xs)
     assert (x[0].cpu() - want_x).abs().max().item() < TOL
     noise = torch.randn(1, 1, 256, 12, 20, generator=torch.Generator().manual_seed(54))
-    out = model.engine().sample(x[0], noise.cuda())
-    ref = O.sample(Wd, ocfg, want_x, noise)
-    assert (out.cpu() - ref).abs().max().item() < 5e-4
-    assert (out.cpu().argmax(1) != ref.argmax(1)).float().mean().item() < 2e-3
+    # the loop on the CUDA neck's own output, against the oracle loop on the SAME tensor (fp64-adjudicated rule of
+    # tests/parity.py: no tolerance on class maps beyond adjudicated ties)
+    import parity as P
+    P.check_seg_parity(model.engine(), Wd, ocfg, x[0].cpu(), noise, "fused neck -> decode loop")
 
 
 def test_neck_error_behaviour():

@@ -58,11 +58,23 @@ def run_neck(a):
     in_bytes = sum(x.numel() * 4 for x in xs)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if in_bytes < (192 << 20) else None
     ms = timed(lambda: eng.forward(xs), a.steps, flush)
+    # per-call device times (events around single calls) next to the back-to-back average above
+    per_call = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        eng.forward(xs)
+        e1.record()
+        torch.cuda.synchronize()
+        per_call.append(round(e0.elapsed_time(e1), 3))
     fl = neck_flops(a.channels, a.h, a.w) * a.images
     print(json.dumps({"row": "neck (FPN + MultiStageMerging)", "images": a.images, "tokens": [a.h, a.w],
                       "in_channels": a.channels, "ms_per_call": ms, "images_per_s": a.images / (ms / 1e3),
                       "algorithmic_tflops": fl / (ms / 1e3) / 1e12, "launches": eng.last_launch_count,
-                      "arithmetic": "fp32 CUDA-core GEMMs (first path)",
+                      "single_call_ms": per_call,
+                      "arithmetic": "3x3 convs: tc_3xf16 tcgen05 implicit GEMM; 1x1 convs: fp32 CUDA-core GEMM"
+                      if os.environ.get("DDP_B200_NECK_TC", "1") != "0" else "fp32 CUDA-core GEMMs (first path)",
                       "l2": "flushed before every call" if flush is not None else "inputs larger than L2"}))
 
 
