@@ -1563,12 +1563,38 @@ int ddp_sample_host_submit(ddp_handle* h, const float* x_host, const float* nois
         CUDA_TRY(h, cudaEventRecord(h->host_ev[0], st));
         CUDA_TRY(h, cudaStreamWaitEvent(h->h2d_stream, h->host_ev[0], 0));
     }
-    CUDA_TRY(h, cudaMemcpyAsync(sx, x_host, B * kE * N * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
-    CUDA_TRY(h, cudaMemcpyAsync(sn, noise_host, rows * cin * N * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
-    CUDA_TRY(h, cudaEventRecord(sl.h2d, h->h2d_stream));
-    CUDA_TRY(h, cudaStreamWaitEvent(st, sl.h2d, 0));
+    // With another call in flight this call's upload hides under that call's loop: one piece.  With an EMPTY pipeline
+    // (first call, or the caller waited for everything) the upload would be exposed: cut the batch in two groups of images
+    // so that only the first group's upload is (the rule of ddp_sample_host_ex).
+    const size_t R = h->R, x_img = kE * N, n_img = R * cin * N, o_img = cout * N;
+    int nchunk = 1;
+    if (!h->slot[si ^ 1].busy) {
+        nchunk = h->host_chunks > 0 ? h->host_chunks
+                                    : ((B * (x_img + n_img) * sizeof(float) >= ((size_t)64 << 20) && B >= 4 && (B / 2) * R * N >= 32768) ? 2 : 1);
+        if (nchunk > (int)B) nchunk = (int)B;
+        if (nchunk > 8) nchunk = 8;
+    }
+    if ((rc = host_pipeline_resources(h, nchunk + 1))) return rc;
+    int b0s[8], nbs[8];
+    for (int i = 0, b0 = 0; i < nchunk; ++i) {
+        nbs[i] = (int)B / nchunk + (i >= nchunk - (int)B % nchunk ? 1 : 0);
+        b0s[i] = b0;
+        b0 += nbs[i];
+    }
+    for (int i = 0; i < nchunk; ++i) {
+        const size_t b0 = b0s[i], nb = nbs[i];
+        CUDA_TRY(h, cudaMemcpyAsync(sx + b0 * x_img, x_host + b0 * x_img, nb * x_img * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaMemcpyAsync(sn + b0 * n_img, noise_host + b0 * n_img, nb * n_img * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+        CUDA_TRY(h, cudaEventRecord(i == nchunk - 1 ? sl.h2d : h->host_ev[1 + i], h->h2d_stream));
+    }
     h->launches = 0;
-    if ((rc = sample_slice(h, sx, sn, so, sc, workspace, 0, (int)B, st))) return rc;
+    for (int i = 0; i < nchunk; ++i) {
+        const size_t b0 = b0s[i], nb = nbs[i];
+        CUDA_TRY(h, cudaStreamWaitEvent(st, i == nchunk - 1 ? sl.h2d : h->host_ev[1 + i], 0));
+        if ((rc = sample_slice(h, sx + b0 * x_img, sn + b0 * n_img, so + b0 * o_img, sc ? sc + b0 * N : nullptr, workspace, (int)b0, (int)nb, st)))
+            return rc;
+    }
+    h->cur_B = h->B; h->cur_rows = h->rows;
     CUDA_TRY(h, cudaEventRecord(sl.done, st));
     CUDA_TRY(h, cudaStreamWaitEvent(h->d2h_stream, sl.done, 0));
     CUDA_TRY(h, cudaMemcpyAsync(out_host, so, B * cout * N * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));

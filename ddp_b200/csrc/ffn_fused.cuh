@@ -280,15 +280,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
                         const uint32_t ui = ring_wait();
                         if (elect_one()) {
+                            // K block kb of the identity holds 2^shift on rows (= output channels) [64 kb, 64 kb + 64) and
+                            // zeros elsewhere: only output half nh = kb / 2 receives anything, the other half's MMAs
+                            // would add exact zeros and are skipped (half of the residual's tensor work)
+                            const int nh = kb >> 1;
+                            const uint64_t bi = make_smem_desc(ui + nh * kPlaneB);
+                            const uint32_t d = tD2 + nh * 128;
 #pragma unroll
-                            for (int nh = 0; nh < 2; ++nh) {
-                                const uint64_t bi = make_smem_desc(ui + nh * kPlaneB);
-                                const uint32_t d = tD2 + nh * 128;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (NSPLIT > 1) mma_ss(d, alo + 2 * k, bi + 2 * k, 1u);
-                                    mma_ss(d, ahi + 2 * k, bi + 2 * k, 1u);
-                                }
+                            for (int k = 0; k < 4; ++k) {
+                                if (NSPLIT > 1) mma_ss(d, alo + 2 * k, bi + 2 * k, 1u);
+                                mma_ss(d, ahi + 2 * k, bi + 2 * k, 1u);
                             }
                         }
                         __syncwarp();

@@ -92,10 +92,14 @@ def closed_loop_seg(eng, W, cfg, x, noise, what, ddpm_noise=None):
                 ga, ra = lg.argmax(1), l32.argmax(1)
                 bad = ga != ra
                 if bad.any():
-                    st64 = O.step_seg_one(W64, cfg, xr.double(), state_in.double(), k, None if nk is None else nk.double(),
-                                          sched_dtype=torch.float32)
-                    l64 = st64["logits"]
-                    disc = (l32.double() - l64).abs().amax(1)                 # (R,h,w): per-pixel fp32-vs-fp64 discrepancy
+                    # fp64 adjudicator, only for the samples (rows) that have a differing pixel: rows are independent
+                    rsel = bad.flatten(1).any(1).nonzero().flatten()
+                    st64 = O.step_seg_one(W64, cfg, xr[rsel].double(), state_in[rsel].double(), k,
+                                          None if nk is None else nk[rsel].double(), sched_dtype=torch.float32)
+                    l64 = torch.zeros(l32.shape, dtype=torch.float64)
+                    l64[rsel] = st64["logits"]
+                    disc = torch.zeros(bad.shape, dtype=torch.float64)
+                    disc[rsel] = (l32[rsel].double() - l64[rsel]).abs().amax(1)     # per-pixel fp32-vs-fp64 discrepancy
                     floor = float(disc.max())
                     # how far below its own maximum the fp32 oracle rates the class the CUDA path chose (for a plain top-2
                     # swap this is the oracle's top-2 margin; at a three-way near-tie the CUDA class may be the third)
