@@ -378,6 +378,10 @@ def measure(name, wl, args, ctx, steps, warmup, with_clocks=False):
         if t is not None and wl["per_gpu"] == WORKLOADS[name]["per_gpu"]:
             roof["traffic"] = t
             roof["traffic_source"] = "profiles/ncu_traffic.json: " + str(tj.get("_source", "ncu --set full capture"))
+    if gemm_like and args.gemm == "tc_3xf16":
+        # fp32-faithful arithmetic on fp16 tensor cores issues three MMAs per algorithmic product: `frac`
+        # counts the algorithmic FLOPs once, so its ceiling is 1/3; this is the tensor pipe's share of ITS ceiling
+        roof["issued_mma_frac"] = 3 * roof["frac"]
     roof["algorithmic_bytes"] = by * tokens_per_launch
     roof["avg_launch_ms"] = 1e3 * avg_s
     roof["launches_timed"] = dcount

@@ -21,7 +21,7 @@ TAP_HEAD_IN, TAP_VALUE, TAP_SAMPLING, TAP_GATHERED, TAP_LN1, TAP_LAYER_OUT, TAP_
 
 EXPORTS = ["ddp_abi_version", "ddp_create", "ddp_destroy", "ddp_last_error", "ddp_weight_count",
            "ddp_weight_name", "ddp_set_weight", "ddp_commit_weights", "ddp_set_schedule",
-           "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_set_uncertainty_outputs", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_sample_host_ex", "ddp_sample_host_submit", "ddp_sample_host_wait", "ddp_head_forward", "ddp_resize_argmax", "ddp_add_tap",
+           "ddp_get_schedule", "ddp_set_ddpm_schedule", "ddp_set_step_noise", "ddp_set_uncertainty_outputs", "ddp_plan", "ddp_sample", "ddp_sample_host", "ddp_sample_host_ex", "ddp_sample_host_submit", "ddp_sample_host_wait", "ddp_head_forward", "ddp_resize_argmax", "ddp_tail_probs", "ddp_probs_argmax", "ddp_add_tap",
            "ddp_set_state_override", "ddp_clear_debug", "ddp_last_launch_count", "ddp_profile_enable",
            "ddp_profile_collect", "ddp_kernel_class_name", "ddp_graph_replays", "ddp_graph_captures", "ddp_graph_last_fallback",
            "ddp_neck_create", "ddp_neck_destroy", "ddp_neck_last_error", "ddp_neck_weight_count", "ddp_neck_weight_name",
@@ -103,6 +103,8 @@ def load():
     lib.ddp_sample_host_wait.argtypes = [vp, i64]
     lib.ddp_head_forward.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     lib.ddp_resize_argmax.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.ddp_tail_probs.argtypes = [vp, vp] + [i32] * 13 + [vp, vp]
+    lib.ddp_probs_argmax.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.ddp_add_tap.argtypes = [vp, i32, i32, i32, vp]
     lib.ddp_set_state_override.argtypes = [vp, i32, vp]
     lib.ddp_clear_debug.argtypes = [vp]

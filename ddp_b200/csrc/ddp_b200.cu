@@ -100,6 +100,7 @@ struct ddp_handle {
 
     // plan
     int B = 0, R = 0, H = 0, W = 0, N = 0, rows = 0;
+    int planned_grid_h = 0, planned_grid_w = 0;    // token grid the shape-only constants in p_arena were built for
     float* p_arena = nullptr;
     float *pe = nullptr, *pew[kMaxLayers] = {nullptr};
     float *d_time_in = nullptr, *four = nullptr, *h1 = nullptr, *temb = nullptr, *film = nullptr;
@@ -816,6 +817,7 @@ int ddp_commit_weights(ddp_handle* h) {
     h->graph_warm_key = ddp_handle::GraphKey();
     h->committed = true;
     h->planned = false;
+    h->planned_grid_h = h->planned_grid_w = 0;          // PE * W and the time tables depend on the weights: rebuild at the next plan
     return DDP_OK;
 }
 
@@ -888,7 +890,12 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     CUDA_TRY(h, cudaSetDevice(h->device));
     const ddp_config& c = h->cfg;
     const int T = c.timesteps, Lc = c.num_layers, N = height * width;
+    // the shape-only constants (positional encoding, its projections, time tables) depend on (h, w) alone: a re-plan
+    // that only changes the batch or the number of samples keeps them — no cudaFree / cudaMalloc / recompute / sync,
+    // which is what a latency-mode caller with a varying batch sees ("weak" 11)
+    const bool same_grid = h->p_arena != nullptr && h->planned_grid_h == height && h->planned_grid_w == width;
     h->B = B; h->R = R; h->H = height; h->W = width; h->N = N; h->rows = B * R;
+    if (!same_grid) {
     if (h->p_arena) { cudaFree(h->p_arena); h->p_arena = nullptr; }
     size_t fl = 0;
     auto need = [&](size_t n) { fl += align_up(n * sizeof(float), 256) / sizeof(float); };
@@ -921,6 +928,8 @@ int ddp_plan(ddp_handle* h, int B, int R, int height, int width, size_t* workspa
     int rc = compute_time_constants(h, st);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->planned_grid_h = height; h->planned_grid_w = width;
+    }
     h->map_cache.clear();
     for (auto& sl : h->slot) { sl.busy = false; sl.used = false; }
     h->ws_bytes = carve(h, nullptr, nullptr, &h->ws_compute_bytes);
@@ -1430,6 +1439,36 @@ int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((out_w + 127) / 128, out_h, B);
     KLAUNCH(h, DDP_K_FINALIZE, st, (k_resize_argmax<<<grid, 128, 0, st>>>(logits, cls, C, in_h, in_w, out_h, out_w)));
+    return DDP_OK;
+}
+
+int ddp_tail_probs(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int img_h, int img_w, int crop_h,
+                   int crop_w, int out_h, int out_w, int rescale, int flip, int accumulate, float* probs, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!logits || !probs) return fail(h, DDP_ERR_INVALID, "ddp_tail_probs: null pointer");
+    if (B < 1 || B > 65535 || C < 1 || C > 256 || in_h < 1 || in_w < 1 || img_h < 1 || img_w < 1 || out_h < 1 || out_w < 1 || out_h > 65535)
+        return fail(h, DDP_ERR_INVALID, "ddp_tail_probs: bad shape");
+    if (flip < 0 || flip > 2) return fail(h, DDP_ERR_INVALID, "ddp_tail_probs: flip must be 0 (none), 1 (horizontal) or 2 (vertical)");
+    if (rescale && (crop_h < 1 || crop_w < 1 || crop_h > img_h || crop_w > img_w))
+        return fail(h, DDP_ERR_INVALID, "ddp_tail_probs: the crop (img_shape) must lie inside the network input size");
+    if (!rescale && (out_h != img_h || out_w != img_w))
+        return fail(h, DDP_ERR_INVALID, "ddp_tail_probs: without rescale the output has the network input size");
+    TailParams t;
+    t.logits = logits; t.probs = probs; t.C = C; t.h = in_h; t.w = in_w; t.img_h = img_h; t.img_w = img_w;
+    t.crop_h = crop_h; t.crop_w = crop_w; t.H = out_h; t.W = out_w; t.rescale = rescale ? 1 : 0; t.flip = flip; t.accumulate = accumulate ? 1 : 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((out_w + 127) / 128, out_h, B);
+    KLAUNCH(h, DDP_K_FINALIZE, st, (k_tail_probs<<<grid, 128, 0, st>>>(t)));
+    return DDP_OK;
+}
+
+int ddp_probs_argmax(ddp_handle* h, const float* probs, int B, int C, int H, int W, uint8_t* cls, void* stream) {
+    if (!h) return DDP_ERR_INVALID;
+    if (!probs || !cls) return fail(h, DDP_ERR_INVALID, "ddp_probs_argmax: null pointer");
+    if (B < 1 || B > 65535 || C < 1 || C > 256 || H < 1 || H > 65535 || W < 1) return fail(h, DDP_ERR_INVALID, "ddp_probs_argmax: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((W + 127) / 128, H, B);
+    KLAUNCH(h, DDP_K_FINALIZE, st, (k_probs_argmax<<<grid, 128, 0, st>>>(probs, cls, C, H, W)));
     return DDP_OK;
 }
 

@@ -451,6 +451,75 @@ __global__ void k_resize_argmax(const float* __restrict__ logits, uint8_t* __res
     cls[((size_t)b * H + y) * W + x] = (uint8_t)bi;
 }
 
+// Whole inference() tail of one (possibly augmented) view (encoder_decoder.py:229-283, ddp.py:124-128) in one pass:
+//   logits (B,C,h,w) --bilinear--> (img_h,img_w) [encode_decode] --crop to (crop_h,crop_w), bilinear--> (H,W) [whole_inference,
+//   rescale=True; skipped when rescale == 0] --softmax over C--> flip back --> probs (B,C,H,W), overwritten or accumulated
+//   (aug_test sums the views).  The two resizes are evaluated nested, each with ATen's upsample_bilinear2d arithmetic
+//   (align_corners=False), so the intermediate image is never materialised but every intermediate value is rounded as
+//   the reference rounds it.
+struct TailParams {
+    const float* logits; float* probs;
+    int C, h, w, img_h, img_w, crop_h, crop_w, H, W;
+    int rescale, flip, accumulate;       // flip: 0 none, 1 horizontal, 2 vertical
+};
+__device__ __forceinline__ void tail_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float f = __fadd_rn(__fmul_rn(scale, (float)dst + 0.5f), -0.5f);
+    f = f < 0.f ? 0.f : f;
+    i0 = (int)f;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = f - (float)i0;
+}
+__device__ __forceinline__ float tail_lerp4(float v00, float v01, float v10, float v11, float ly, float lx) {
+    const float hy = 1.0f - ly, hx = 1.0f - lx;
+    return __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01))),
+                     __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11))));
+}
+// value of the img-size map (first resize) at (Y, X) for one class plane
+__device__ __forceinline__ float tail_stage1(const float* __restrict__ p, int Y, int X, const TailParams& t) {
+    int y0, y1, x0, x1; float ly, lx;
+    tail_src(Y, (float)t.h / (float)t.img_h, t.h, y0, y1, ly);
+    tail_src(X, (float)t.w / (float)t.img_w, t.w, x0, x1, lx);
+    return tail_lerp4(p[y0 * t.w + x0], p[y0 * t.w + x1], p[y1 * t.w + x0], p[y1 * t.w + x1], ly, lx);
+}
+__global__ void __launch_bounds__(128) k_tail_probs(TailParams t) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= t.W) return;
+    int Y0 = y, Y1 = y, X0 = x, X1 = x; float LY = 0.f, LX = 0.f;
+    if (t.rescale) {
+        tail_src(y, (float)t.crop_h / (float)t.H, t.crop_h, Y0, Y1, LY);
+        tail_src(x, (float)t.crop_w / (float)t.W, t.crop_w, X0, X1, LX);
+    }
+    const float* base = t.logits + (size_t)b * t.C * t.h * t.w;
+    auto value = [&](int c) -> float {
+        const float* p = base + (size_t)c * t.h * t.w;
+        if (!t.rescale) return tail_stage1(p, y, x, t);
+        return tail_lerp4(tail_stage1(p, Y0, X0, t), tail_stage1(p, Y0, X1, t), tail_stage1(p, Y1, X0, t), tail_stage1(p, Y1, X1, t), LY, LX);
+    };
+    float mx = -INFINITY;
+    for (int c = 0; c < t.C; ++c) mx = fmaxf(mx, value(c));
+    float sum = 0.f;
+    for (int c = 0; c < t.C; ++c) sum += expf(value(c) - mx);
+    const int xo = t.flip == 1 ? t.W - 1 - x : x, yo = t.flip == 2 ? t.H - 1 - y : y;
+    float* o = t.probs + ((size_t)b * t.C * t.H + yo) * t.W + xo;
+    for (int c = 0; c < t.C; ++c) {
+        const float pr = __fdiv_rn(expf(value(c) - mx), sum);
+        float* oc = o + (size_t)c * t.H * t.W;
+        *oc = t.accumulate ? *oc + pr : pr;
+    }
+}
+// class map of accumulated probabilities: argmax over C (first maximum wins, as torch.argmax)
+__global__ void __launch_bounds__(128) k_probs_argmax(const float* __restrict__ probs, uint8_t* __restrict__ cls, int C, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= W) return;
+    const float* p = probs + ((size_t)b * C * H + y) * W + x;
+    float best = -INFINITY; int bi = 0;
+    for (int c = 0; c < C; ++c) {
+        const float v = p[(size_t)c * H * W];
+        if (v > best) { best = v; bi = c; }
+    }
+    cls[((size_t)b * H + y) * W + x] = (uint8_t)bi;
+}
+
 struct DepthStepParams {
     const float* taps;     // [rows][N][16]: per-token dot products with the 9 conv3x3 taps (cols 0..8)
     float* state;          // [rows][N] depth_t in/out

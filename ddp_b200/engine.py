@@ -130,7 +130,9 @@ class DecodeEngine:
         nbytes = ctypes.c_size_t()
         with torch.cuda.device(self.device):
             self._check(self.lib.ddp_plan(self._h, B, R, h, w, ctypes.byref(nbytes)))
-            self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+            if self._ws is None or self._ws.numel() < nbytes.value + 256:      # a smaller plan reuses the workspace
+                self._ws = None
+                self._ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
         self._ws_bytes = nbytes.value
         self._plan = key
 
@@ -217,6 +219,35 @@ class DecodeEngine:
         stream = torch.cuda.current_stream(logits.device).cuda_stream
         with torch.cuda.device(self.device):
             self._check(self.lib.ddp_resize_argmax(self._h, logits.data_ptr(), B, C, h, w, H, W, cls.data_ptr(), stream))
+        return cls
+
+    def tail_probs(self, logits: torch.Tensor, img_size, crop=None, out_size=None, flip=None, accum: Optional[torch.Tensor] = None):
+        """inference() tail of one view in one kernel: (B,C,h,w) logits -> resize to `img_size` -> [crop to `crop`, resize to
+        `out_size`] -> softmax -> flip back ('horizontal' / 'vertical') -> (B,C,H,W) probabilities; added into `accum` when
+        given (aug_test), else returned in a new tensor."""
+        B, C, h, w = logits.shape
+        self._on_device(logits, accum)
+        logits = logits.contiguous()
+        ih, iw = int(img_size[0]), int(img_size[1])
+        rescale = out_size is not None
+        ch, cw = (int(crop[0]), int(crop[1])) if crop is not None else (ih, iw)
+        H, W = (int(out_size[0]), int(out_size[1])) if rescale else (ih, iw)
+        fl = {None: 0, False: 0, "horizontal": 1, "vertical": 2}[flip]
+        probs = accum if accum is not None else torch.empty((B, C, H, W), dtype=torch.float32, device=logits.device)
+        assert tuple(probs.shape) == (B, C, H, W) and probs.dtype == torch.float32 and probs.is_contiguous()
+        stream = torch.cuda.current_stream(logits.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_tail_probs(self._h, logits.data_ptr(), B, C, h, w, ih, iw, ch, cw, H, W, int(rescale), fl,
+                                                int(accum is not None), probs.data_ptr(), stream))
+        return probs
+
+    def probs_argmax(self, probs: torch.Tensor):
+        B, C, H, W = probs.shape
+        self._on_device(probs)
+        cls = torch.empty((B, H, W), dtype=torch.uint8, device=probs.device)
+        stream = torch.cuda.current_stream(probs.device).cuda_stream
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ddp_probs_argmax(self._h, probs.contiguous().data_ptr(), B, C, H, W, cls.data_ptr(), stream))
         return cls
 
     def sample_host(self, x: torch.Tensor, noise: torch.Tensor, out: Optional[torch.Tensor] = None,

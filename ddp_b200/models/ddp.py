@@ -246,11 +246,32 @@ class DDP(_DiffusionSegmentorBase):
             seg_logit = resize(seg_logit, size=size, mode="bilinear", align_corners=self.align_corners, warning=False)
         return seg_logit
 
+    def _fused_view(self, img, img_meta, rescale, accum=None):
+        """encode_decode + whole_inference + softmax + flip of `inference` for one view as ONE kernel after the loop
+        (ddp_tail_probs): probabilities (b,C,H,W), added into `accum` when given.  None when the view needs the eager path
+        (align_corners=True heads, the ddpm sampler's own noise bookkeeping, a head with one output channel)."""
+        if not self.fused_tail or self.align_corners or self.out_channels == 1 or (self.test_cfg or {}).get("mode", "whole") != "whole":
+            return None
+        x = self.extract_feat(img)[0]
+        logits = self.ddim_sample(x, img_meta) if self.diffusion == "ddim" else self.ddpm_sample(x, img_meta)
+        meta = img_meta[0]
+        flip = meta.get("flip_direction", "horizontal") if meta.get("flip", False) else None
+        assert flip in (None, "horizontal", "vertical")
+        if rescale:
+            return self.engine().tail_probs(logits, img.shape[2:], crop=meta["img_shape"][:2], out_size=meta["ori_shape"][:2],
+                                            flip=flip, accum=accum)
+        return self.engine().tail_probs(logits, img.shape[2:], flip=flip, accum=accum)
+
     def inference(self, img, img_meta, rescale):
         mode = (self.test_cfg or {}).get("mode", "whole")
         assert mode in ["slide", "whole"]
         if mode == "slide":
             raise NotImplementedError("slide inference is not used by any DDP config")
+        ori_shape = img_meta[0]["ori_shape"] if "ori_shape" in img_meta[0] else None
+        assert all(m.get("ori_shape") == ori_shape for m in img_meta)
+        fused = self._fused_view(img, img_meta, rescale)
+        if fused is not None:
+            return fused
         seg_logit = self.whole_inference(img, img_meta, rescale)
         output = F.softmax(seg_logit, dim=1)
         if img_meta[0].get("flip", False):
@@ -277,10 +298,17 @@ class DDP(_DiffusionSegmentorBase):
         return list(seg_pred.cpu().numpy())
 
     def aug_test(self, imgs, img_metas, rescale=True):
+        """encoder_decoder.py:295-304: the views' probability maps are summed (here: accumulated in place by the tail kernel,
+        one launch per view), divided by their number and arg-maxed (the division does not change the argmax)."""
         assert rescale
         seg_logit = self.inference(imgs[0], img_metas[0], rescale)
+        fused = self.fused_tail and not self.align_corners and self.out_channels != 1
         for i in range(1, len(imgs)):
+            if fused and self._fused_view(imgs[i], img_metas[i], rescale, accum=seg_logit) is not None:
+                continue
             seg_logit += self.inference(imgs[i], img_metas[i], rescale)
+        if fused:
+            return list(self.engine().probs_argmax(seg_logit).cpu().numpy().astype("int64"))
         seg_logit /= len(imgs)
         return list(seg_logit.argmax(dim=1).cpu().numpy())
 

@@ -174,6 +174,17 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
 int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int out_h, int out_w,
                       uint8_t* cls, void* stream);
 
+/* The general inference() tail of one view, for flipped / rescaled / multi-scale test-time augmentation
+ * (encoder_decoder.py:229-283 whole_inference + inference, ddp.py:124-128; aug_test :295-304 sums the views):
+ *   logits (B,C,in_h,in_w) --bilinear--> (img_h,img_w) --[rescale: crop to (crop_h,crop_w) = img_meta img_shape, bilinear to
+ *   (out_h,out_w) = ori_shape]--> softmax over C --> flip back (1 horizontal, 2 vertical) --> probs (B,C,out_h,out_w) fp32,
+ * overwritten (accumulate = 0) or added to (accumulate = 1).  Both resizes use align_corners=False and are evaluated
+ * nested in one kernel with the reference's rounding of the intermediate image.  ddp_probs_argmax turns (accumulated)
+ * probabilities into the uint8 class map. */
+int ddp_tail_probs(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int img_h, int img_w, int crop_h,
+                   int crop_w, int out_h, int out_w, int rescale, int flip, int accumulate, float* probs, void* stream);
+int ddp_probs_argmax(ddp_handle* h, const float* probs, int B, int C, int H, int W, uint8_t* cls, void* stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies x and noise to the device, runs
  * ddp_sample, copies out (and cls) back and synchronises the stream.  Uses the tail of the workspace
  * for staging (ddp_plan's size already includes it). */

@@ -469,6 +469,50 @@ def test_fused_post_loop_tail_matches_torch():
         assert diff.float().mean().item() < 1e-4
 
 
+def test_fused_inference_tail_flip_rescale_and_aug_test():
+    """ddp_tail_probs / ddp_probs_argmax behind `inference` and `aug_test` (encoder_decoder.py:229-304): resize to the
+    network input size, crop to img_shape, resize to ori_shape, softmax, flip back, sum over augmented views — against the
+    eager torch path of the same plug-in on the same logits (same seed => same noise)."""
+    model = _toy_model(timesteps=2)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    model.load_state_dict(O.make_weights(cfg, seed=71), strict=False)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+
+    def both(fn):
+        model.fused_tail = True
+        torch.manual_seed(9)
+        a = fn()
+        model.fused_tail = False
+        torch.manual_seed(9)
+        b = fn()
+        model.fused_tail = True
+        return a, b
+
+    views = [((64, 96), (60, 90), False, None), ((96, 128), (90, 128), True, "horizontal"), ((48, 64), (48, 61), True, "vertical")]
+    ori = (75, 110, 3)
+    imgs, metas = [], []
+    for (ih, iw), (ch, cw), flip, d in views:
+        imgs.append(torch.randn(1, 3, ih, iw, generator=g).cuda())
+        metas.append([dict(img_shape=(ch, cw, 3), ori_shape=ori, pad_shape=(ih, iw, 3), flip=flip, flip_direction=d)])
+    for img, meta in zip(imgs, metas):
+        for rescale in (True, False):
+            a, b = both(lambda: model.inference(img, meta, rescale))
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() < 2e-6, (meta, rescale, (a - b).abs().max().item())
+            assert (a.sum(1) - 1).abs().max().item() < 1e-5
+    a, b = both(lambda: model.aug_test(imgs, metas, rescale=True))
+    assert a[0].shape == (75, 110) and b[0].shape == (75, 110)
+    diff = torch.from_numpy(a[0] != b[0])
+    if diff.any():          # only ties of the summed probabilities (inside their 1e-6 rounding) may differ
+        model.fused_tail = False
+        torch.manual_seed(9)
+        psum = sum(model.inference(i, m, True) for i, m in zip(imgs, metas))[0].cpu()
+        model.fused_tail = True
+        top2 = psum.topk(2, dim=0).values
+        assert float((top2[0] - top2[1])[diff].max()) < 1e-5
+
+
 def test_unfused_ffn_pair_still_correct(monkeypatch):
     """DDP_B200_FUSE_FFN=0 selects the separate FFN1 (16-warp GELU epilogue) and FFN2 (LN + FiLM epilogue) kernels."""
     monkeypatch.setenv("DDP_B200_FUSE_FFN", "0")
@@ -606,6 +650,28 @@ def test_uncertainty_maps_match_oracle_definition(case):
         own = tap.view(B, R, N).std(1, unbiased=False).view(B, case["h"], case["w"])
         eng.clear_debug()
         assert (unc2["spread"] - own).abs().max().item() < 1e-6
+
+
+def test_replan_keeps_shape_constants_and_results():
+    """A re-plan that only changes the batch / sample count reuses the shape-only constants (no realloc); changing the
+    grid or the weights rebuilds them.  Results must be what a fresh engine gives."""
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2, randsteps=2)
+    W = O.make_weights(cfg, seed=61)
+    W2 = O.make_weights(cfg, seed=62)
+    x, noise = O.make_inputs(cfg, 3, 8, 12, seed=63)
+    x2, noise2 = O.make_inputs(cfg, 1, 6, 10, seed=64)
+    eng = make_engine(cfg, W, "tc_3xf16")
+    a3 = eng.sample(x.cuda(), noise.cuda())
+    a1 = eng.sample(x[:1].cuda(), noise[:1].cuda())                      # batch 3 -> 1, same grid
+    a1r = eng.sample(x[:1].cuda(), noise[:1, :1].cuda())                 # R 2 -> 1
+    b = eng.sample(x2.cuda(), noise2.cuda())                             # other grid
+    a3b = eng.sample(x.cuda(), noise.cuda())                             # back
+    assert torch.equal(a3, a3b) and torch.equal(a1, a3[:1])
+    fresh = make_engine(cfg, W, "tc_3xf16")
+    assert torch.equal(fresh.sample(x2.cuda(), noise2.cuda()), b)
+    assert torch.equal(fresh.sample(x[:1].cuda(), noise[:1, :1].cuda()), a1r)
+    eng.load_state_dict(W2)                                              # new weights: PE * W must be rebuilt
+    assert torch.equal(eng.sample(x.cuda(), noise.cuda()), make_engine(cfg, W2, "tc_3xf16").sample(x.cuda(), noise.cuda()))
 
 
 def test_empty_batch():
