@@ -74,6 +74,7 @@ struct ddp_handle {
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
     bool qproj_fused = false;   // value + sampling projections in one kernel (qproj_fused.cuh), DDP_B200_QPROJ_FUSED
+    bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
     int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
     unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
@@ -85,7 +86,8 @@ struct ddp_handle {
     int out_bn = 32;
     // activation TMA maps of the ACTIVE batch slice (copied from the cache below by ensure_activation_maps)
     CUtensorMap mA_state[2], mA_q[2], mA_g[2], mA_hid[2];
-    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2]; };
+    CUtensorMap mS_V, mS_rec;           // TMA STORE maps of the value tensor and the sampling records (qproj_fused epilogue)
+    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2], vout, rec; };
     std::vector<ActMaps> map_cache;     // one entry per (workspace, first image, image count) a call has used since ddp_plan
     int cur_B = 0, cur_rows = 0;        // images / rows of the slice the launches below work on (== B, rows unless ddp_sample_host chunks)
 
@@ -598,6 +600,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     auto activate = [&](const ddp_handle::ActMaps& a) {
         memcpy(h->mA_state, a.state, sizeof(a.state)); memcpy(h->mA_q, a.q, sizeof(a.q));
         memcpy(h->mA_g, a.g, sizeof(a.g)); memcpy(h->mA_hid, a.hid, sizeof(a.hid));
+        h->mS_V = a.vout; h->mS_rec = a.rec;
     };
     for (const auto& a : h->map_cache)
         if (a.ws == ws_base && a.b0 == b0 && a.nb == nb) { activate(a); return DDP_OK; }
@@ -612,6 +615,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     ok = ok && tc::make_map_f16(&a.q[0], ws.q_hi, M, kE, tc::BM) && tc::make_map_f16(&a.q[1], ws.q_lo, M, kE, tc::BM);
     ok = ok && tc::make_map_f16(&a.g[0], ws.g_hi, M, kE, tc::BM) && tc::make_map_f16(&a.g[1], ws.g_lo, M, kE, tc::BM);
     ok = ok && tc::make_map_f16(&a.hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&a.hid[1], ws.hid_lo, M, kFFN, tc::BM);
+    ok = ok && tc::make_store_map_32bit(&a.vout, ws.V, M, kE, 16, true) && tc::make_store_map_32bit(&a.rec, ws.rec, M, kRecW, 8, false);
     if (!ok) return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation plane");
     h->map_cache.push_back(a);
     activate(a);
@@ -678,6 +682,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* ts = getenv("DDP_B200_QPROJ_TMA_STORES");
+        h->qproj_tma_stores = ts == nullptr || atoi(ts) != 0;           // default on; 0 = per-thread staged stores
         const char* hc = getenv("DDP_B200_HOST_CHUNKS");
         h->host_chunks = hc ? atoi(hc) : 0;                             // ddp_sample_host pipeline depth (0 = automatic)
         const char* gr = getenv("DDP_B200_GRAPH");
@@ -997,11 +1003,12 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 qp.scale_v = T.v.inv_scale; qp.bias_v = L.bv; qp.V = ws.V;
                 qp.samp.scale = T.s.inv_scale; qp.samp.out = want_s ? ws.samp : nullptr; qp.samp.ldc = kSampW; qp.samp.ncols = kSampW;
                 qp.samp.pew = h->pew[j]; qp.samp.N_tok = N; qp.samp.rec = ws.rec; qp.samp.H = h->H; qp.samp.W = h->W;
+                qp.tma_stores = h->qproj_tma_stores ? 1 : 0;
                 prof_begin(h, DDP_K_QPROJ_FUSED, st);
                 cudaError_t e_ = s3 ? tc::launch_qproj_fused<3>(h->mA_q[0], h->mA_q[1], T.v.map_half_hi, T.v.map_half_lo,
-                                                                T.s.map_pair_hi, T.s.map_pair_lo, M, kE, qp, h->num_sms, st)
+                                                                T.s.map_pair_hi, T.s.map_pair_lo, h->mS_V, h->mS_rec, M, kE, qp, h->num_sms, st)
                                     : tc::launch_qproj_fused<1>(h->mA_q[0], h->mA_q[0], T.v.map_half_hi, T.v.map_half_hi,
-                                                                T.s.map_pair_hi, T.s.map_pair_hi, M, kE, qp, h->num_sms, st);
+                                                                T.s.map_pair_hi, T.s.map_pair_hi, h->mS_V, h->mS_rec, M, kE, qp, h->num_sms, st);
                 prof_end(h, st);
                 if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused q-projection setup failed: %s", cudaGetErrorString(e_));
                 LAUNCH_CHECK(h);

@@ -83,6 +83,15 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+// TMA box STORE shared -> global (bulk async group of the issuing thread).  The shared tile must stay untouched until
+// tma_store_wait_read() (same thread) returns; rows / columns outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -388,6 +397,35 @@ __device__ __forceinline__ void stage_store_32b(float* stg, const uint4* h, __ha
     __syncwarp();
 }
 
+// The two staged stores above with the second half (LDS + STG by every thread) replaced by ONE TMA box store issued by
+// lane 0: the XOR patterns of stage_store_f16_32 / stage_store_32b ARE the SWIZZLE_64B / SWIZZLE_32B shared-memory
+// layouts, so the tile can be handed to the TMA unit as it is.  Halves the LSU work of a store-bound epilogue.  The tile is
+// reused by the next call: lane 0 first waits until the previous box store has READ it (stage_tma_sync).
+__device__ __forceinline__ void stage_tma_sync(int lane) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+}
+// 32 rows x 64 bytes; map: box {64 bytes, 32 rows}, SWIZZLE_64B; c0 in ELEMENTS of the map's data type
+__device__ __forceinline__ void stage_tma_store_64(float* stg, const uint4* h, const CUtensorMap* map, int c0, int row0, int lane) {
+    stage_tma_sync(lane);
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s16[lane * 4 + (j ^ ((lane >> 1) & 3))] = h[j];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tma_store_2d(map, stg, c0, row0);
+}
+// 32 rows x 32 bytes; map: box {32 bytes, 32 rows}, SWIZZLE_32B
+__device__ __forceinline__ void stage_tma_store_32(float* stg, const uint4* h, const CUtensorMap* map, int c0, int row0, int lane) {
+    stage_tma_sync(lane);
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+    s16[lane * 2 + (0 ^ ((lane >> 2) & 1))] = h[0];
+    s16[lane * 2 + (1 ^ ((lane >> 2) & 1))] = h[1];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tma_store_2d(map, stg, c0, row0);
+}
+
 struct EpiParams {
     float scale;             // undoes the operand scales: acc * scale = A*W^T
     const float* bias;       // [N] or null
@@ -414,8 +452,10 @@ struct EpiParams {
 // (head, point), 64..95 attention logits, 96..127 padding.  Four warps per TMEM lane quarter: warp `half` (0..3) owns
 // heads 2*half and 2*half + 1, i.e. offset columns [16 half, +16) and logits [64 + 8 half, +8); it writes the matching
 // 32-byte pieces of the four record sections (index words, fx, fy, attention weights).  `stg` = this warp's >= 1 KB tile.
+// rec_map != nullptr: the record pieces leave through TMA box stores (map over rec as [M][128] 32-bit words, box {8, 32},
+// SWIZZLE_32B) instead of per-thread stores; the caller owns the bulk-group discipline of `stg` (stage_tma_sync).
 __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t t_row, int half, int wrow0, size_t srow,
-                                                  int rows_valid, int lane, float* stg) {
+                                                  int rows_valid, int lane, float* stg, const CUtensorMap* rec_map = nullptr) {
     const int n = (int)(srow % ep.N_tok);
     __half* rech = reinterpret_cast<__half*>(ep.rec + (size_t)wrow0 * kRecW);       // 2 halves per record word
     const float* pp = ep.pew + (size_t)n * kSampW;
@@ -435,6 +475,7 @@ __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t 
         a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
     }
     if (ep.out) {                       // raw offsets for the test tap (fp32, 2 x 8 columns)
+        if (rec_map) stage_tma_sync(lane);
         __half* oh = reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 16 * half);
         stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[0]), oh, 2 * ep.ldc, rows_valid, lane);
         stage_store_32b(stg, reinterpret_cast<const uint4*>(&o[8]), oh + 16, 2 * ep.ldc, rows_valid, lane);
@@ -450,9 +491,15 @@ __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t 
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             msda_resolve(o[2 * k], o[2 * k + 1], refx, refy, rW, rH, ep.H, ep.W, wi[k], fxp[k], fyp[k]);
-        stage_store_32b(stg, widx, rech + 2 * (8 * half), 2 * kRecW, rows_valid, lane);
-        stage_store_32b(stg, wfx, rech + 2 * (32 + 8 * half), 2 * kRecW, rows_valid, lane);
-        stage_store_32b(stg, wfy, rech + 2 * (64 + 8 * half), 2 * kRecW, rows_valid, lane);
+        if (rec_map) {
+            stage_tma_store_32(stg, widx, rec_map, 8 * half, wrow0, lane);
+            stage_tma_store_32(stg, wfx, rec_map, 32 + 8 * half, wrow0, lane);
+            stage_tma_store_32(stg, wfy, rec_map, 64 + 8 * half, wrow0, lane);
+        } else {
+            stage_store_32b(stg, widx, rech + 2 * (8 * half), 2 * kRecW, rows_valid, lane);
+            stage_store_32b(stg, wfx, rech + 2 * (32 + 8 * half), 2 * kRecW, rows_valid, lane);
+            stage_store_32b(stg, wfy, rech + 2 * (64 + 8 * half), 2 * kRecW, rows_valid, lane);
+        }
     }
 #pragma unroll
     for (int g = 0; g < 2; ++g) {       // softmax over each head's 4 points
@@ -461,7 +508,9 @@ __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t 
         const float sden = (e0 + e1) + (e2 + e3);
         a[g * 4] = e0 / sden; a[g * 4 + 1] = e1 / sden; a[g * 4 + 2] = e2 / sden; a[g * 4 + 3] = e3 / sden;
     }
-    stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]), rech + 2 * (96 + 8 * half), 2 * kRecW, rows_valid, lane);
+    if (rec_map) stage_tma_store_32(stg, reinterpret_cast<const uint4*>(&a[0]), rec_map, 96 + 8 * half, wrow0, lane);
+    else stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]), rech + 2 * (96 + 8 * half), 2 * kRecW, rows_valid, lane);
+    if (ep.out && rec_map) stage_tma_sync(lane);
     if (ep.out)
         stage_store_32b(stg, reinterpret_cast<const uint4*>(&a[0]),
                         reinterpret_cast<__half*>(ep.out + (size_t)wrow0 * ep.ldc + 64 + 8 * half), 2 * ep.ldc, rows_valid, lane);
@@ -865,6 +914,20 @@ inline bool make_map_f16(CUtensorMap* map, const void* base, uint64_t rows, uint
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 2-D row-major tensor [rows][cols] of 32-bit elements for TMA box STORES from a warp's staging tile:
+// box = [32 rows][box_cols], swizzle 64B (box_cols = 16) or 32B (box_cols = 8)
+inline bool make_store_map_32bit(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, bool is_float) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {box_cols, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, int NSPLIT, int EPI, bool PAIR = false>

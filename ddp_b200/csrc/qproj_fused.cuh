@@ -30,6 +30,7 @@ struct QprojParams {
     const float* bias_v;     // [256]
     float* V;                // [M][256] fp32
     EpiParams samp;          // scale, pew, N_tok, H, W, rec, out (optional raw tap), ldc: as for EPI_SAMPLING
+    int tma_stores;          // 1: the value tile and the records leave through TMA box stores (mapVout / mapRec)
 };
 
 constexpr int kQpThreads = 32 * 19;                   // A producer, MMA issuer, 16 epilogue warps, weight producer
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(kQpThreads, 1)
 qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapVhi, const __grid_constant__ CUtensorMap mapVlo,
                    const __grid_constant__ CUtensorMap mapShi, const __grid_constant__ CUtensorMap mapSlo,
+                   const __grid_constant__ CUtensorMap mapVout, const __grid_constant__ CUtensorMap mapRec,
                    int M, int K, QprojParams p) {
     constexpr int kPl = NSPLIT > 1 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
@@ -77,6 +79,7 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     const int n_kb = K / BK;
 
     if (warp == 0 && lane == 0) {
+        if (p.tma_stores) { tma_prefetch_desc(&mapVout); tma_prefetch_desc(&mapRec); }
         tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapVhi); tma_prefetch_desc(&mapShi);
         if (NSPLIT > 1) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapVlo); tma_prefetch_desc(&mapSlo); }
     }
@@ -204,13 +207,22 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
             const size_t srow = row < M ? (size_t)row : (size_t)(M - 1);
             // ---- value tile: V = acc * scale + bias ----
+            // Both 32-column blocks are pulled into registers FIRST and V's TMEM columns are released at once: V is single
+            // buffered, so the next round's V MMAs wait for this release — with the release after the stores (round 1) the
+            // tensor pipe idled through the whole LSU-bound store phase of every round (ncu source view: 12 % of the
+            // kernel's stall samples sat on the v_full wait, 37 % in the store phase).
             mbar_wait(v_full, vfph); vfph ^= 1;
             tc_fence_after();
-#pragma unroll 1
+            float va[32], vb[32];
+            tmem_ld32(tV + part * 64 + lane_sel, va);
+            tmem_ld32(tV + part * 64 + 32 + lane_sel, vb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(v_empty);              // V's columns may be overwritten by the next round
+#pragma unroll
             for (int c = 0; c < 64; c += 32) {
-                float v[32];
+                float* v = c == 0 ? va : vb;
                 const int col = part * 64 + c;
-                tmem_ld32(tV + col + lane_sel, v);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias_v + col + i * 4));
@@ -218,22 +230,26 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                     v[i * 4 + 2] = fmaf(v[i * 4 + 2], p.scale_v, b4.z); v[i * 4 + 3] = fmaf(v[i * 4 + 3], p.scale_v, b4.w);
                 }
                 // 16 floats = 64-byte rows: the tile geometry of 32 fp16 columns
-                __half* dst = reinterpret_cast<__half*>(p.V + (size_t)wrow0 * kE + col);
-                stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[0]), dst, 2 * kE, rows_valid, lane);
-                stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[16]), dst + 32, 2 * kE, rows_valid, lane);
+                if (p.tma_stores) {
+                    stage_tma_store_64(stg, reinterpret_cast<const uint4*>(&v[0]), &mapVout, col, wrow0, lane);
+                    stage_tma_store_64(stg, reinterpret_cast<const uint4*>(&v[16]), &mapVout, col + 16, wrow0, lane);
+                } else {
+                    __half* dst = reinterpret_cast<__half*>(p.V + (size_t)wrow0 * kE + col);
+                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[0]), dst, 2 * kE, rows_valid, lane);
+                    stage_store_f16_32(stg, reinterpret_cast<const uint4*>(&v[16]), dst + 32, 2 * kE, rows_valid, lane);
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(v_empty);              // V's columns may be overwritten by the next round
             // ---- sampling tile ----
             mbar_wait(&s_full[sbuf], sfph[sbuf]); sfph[sbuf] ^= 1;
             tc_fence_after();
-            sampling_epilogue(p.samp, tS + (uint32_t)sbuf * 128u + lane_sel, part, wrow0, srow, rows_valid, lane, stg);
+            sampling_epilogue(p.samp, tS + (uint32_t)sbuf * 128u + lane_sel, part, wrow0, srow, rows_valid, lane, stg,
+                              p.tma_stores ? &mapRec : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&s_empty[sbuf]);
             sbuf ^= 1;
         }
+        if (p.tma_stores && lane == 0) tma_store_wait_all();         // this thread's box stores are complete before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -247,7 +263,8 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
 // mapV*: value_proj weight planes with 64-row boxes; mapS*: sampling weight planes (128 padded rows) with 64-row boxes
 template <int NSPLIT>
 inline cudaError_t launch_qproj_fused(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& vHi,
-                                      const CUtensorMap& vLo, const CUtensorMap& sHi, const CUtensorMap& sLo, int M, int K,
+                                      const CUtensorMap& vLo, const CUtensorMap& sHi, const CUtensorMap& sLo,
+                                      const CUtensorMap& vOut, const CUtensorMap& recOut, int M, int K,
                                       const QprojParams& p, int num_sms, cudaStream_t st) {
     auto kern = qproj_fused_kernel<NSPLIT>;
     {   // per-device attribute
@@ -272,7 +289,7 @@ inline cudaError_t launch_qproj_fused(const CUtensorMap& aHi, const CUtensorMap&
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, aHi, aLo, vHi, vLo, sHi, sLo, M, K, p);
+    return cudaLaunchKernelEx(&cfg, kern, aHi, aLo, vHi, vLo, sHi, sLo, vOut, recOut, M, K, p);
 }
 
 }  // namespace tc
