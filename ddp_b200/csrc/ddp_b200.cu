@@ -74,6 +74,7 @@ struct ddp_handle {
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
     bool qproj_fused = false;   // value + sampling projections in one kernel (qproj_fused.cuh), DDP_B200_QPROJ_FUSED
+    bool ffn_tma_stores = true;     // DDP_B200_FFN_TMA_STORES: the fused FFN's new q planes leave through TMA box stores
     bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
     int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
@@ -86,8 +87,9 @@ struct ddp_handle {
     int out_bn = 32;
     // activation TMA maps of the ACTIVE batch slice (copied from the cache below by ensure_activation_maps)
     CUtensorMap mA_state[2], mA_q[2], mA_g[2], mA_hid[2];
+    CUtensorMap mS_q[2];                // TMA STORE maps of the q planes (fused FFN epilogue)
     CUtensorMap mS_V, mS_rec;           // TMA STORE maps of the value tensor and the sampling records (qproj_fused epilogue)
-    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2], vout, rec; };
+    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2], vout, rec, qs[2]; };
     std::vector<ActMaps> map_cache;     // one entry per (workspace, first image, image count) a call has used since ddp_plan
     int cur_B = 0, cur_rows = 0;        // images / rows of the slice the launches below work on (== B, rows unless ddp_sample_host chunks)
 
@@ -600,7 +602,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     auto activate = [&](const ddp_handle::ActMaps& a) {
         memcpy(h->mA_state, a.state, sizeof(a.state)); memcpy(h->mA_q, a.q, sizeof(a.q));
         memcpy(h->mA_g, a.g, sizeof(a.g)); memcpy(h->mA_hid, a.hid, sizeof(a.hid));
-        h->mS_V = a.vout; h->mS_rec = a.rec;
+        h->mS_V = a.vout; h->mS_rec = a.rec; h->mS_q[0] = a.qs[0]; h->mS_q[1] = a.qs[1];
     };
     for (const auto& a : h->map_cache)
         if (a.ws == ws_base && a.b0 == b0 && a.nb == nb) { activate(a); return DDP_OK; }
@@ -616,6 +618,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     ok = ok && tc::make_map_f16(&a.g[0], ws.g_hi, M, kE, tc::BM) && tc::make_map_f16(&a.g[1], ws.g_lo, M, kE, tc::BM);
     ok = ok && tc::make_map_f16(&a.hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&a.hid[1], ws.hid_lo, M, kFFN, tc::BM);
     ok = ok && tc::make_store_map_32bit(&a.vout, ws.V, M, kE, 16, true) && tc::make_store_map_32bit(&a.rec, ws.rec, M, kRecW, 8, false);
+    ok = ok && tc::make_store_map_f16_32B(&a.qs[0], ws.q_hi, M, kE) && tc::make_store_map_f16_32B(&a.qs[1], ws.q_lo, M, kE);
     if (!ok) return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation plane");
     h->map_cache.push_back(a);
     activate(a);
@@ -682,6 +685,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* fs = getenv("DDP_B200_FFN_TMA_STORES");
+        h->ffn_tma_stores = fs == nullptr || atoi(fs) != 0;             // default on; 0 = per-thread staged stores
         const char* ts = getenv("DDP_B200_QPROJ_TMA_STORES");
         h->qproj_tma_stores = ts == nullptr || atoi(ts) != 0;           // default on; 0 = per-thread staged stores
         const char* hc = getenv("DDP_B200_HOST_CHUNKS");
@@ -1048,18 +1053,19 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 fp.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                 fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
                 fp.dbg = h->ffn_dbg;
+                fp.tma_stores = h->ffn_tma_stores ? 1 : 0;
                 prof_begin(h, DDP_K_FFN_FUSED, st);
                 cudaError_t e_;
                 if (h->ffn_pair)
                     e_ = s3 ? tc::launch_ffn_fused<3, true>(h->mA_q[0], h->mA_q[1], T.f1.map_half_hi, T.f1.map_half_lo, T.f2.map_half_hi,
-                                                            T.f2.map_half_lo, M, fp, h->num_sms, st)
+                                                            T.f2.map_half_lo, h->mS_q[0], h->mS_q[1], M, fp, h->num_sms, st)
                             : tc::launch_ffn_fused<1, true>(h->mA_q[0], h->mA_q[0], T.f1.map_half_hi, T.f1.map_half_hi, T.f2.map_half_hi,
-                                                            T.f2.map_half_hi, M, fp, h->num_sms, st);
+                                                            T.f2.map_half_hi, h->mS_q[0], h->mS_q[0], M, fp, h->num_sms, st);
                 else
                     e_ = s3 ? tc::launch_ffn_fused<3, false>(h->mA_q[0], h->mA_q[1], T.f1.map_alt_hi, T.f1.map_alt_lo, T.f2.map_alt_hi,
-                                                             T.f2.map_alt_lo, M, fp, h->num_sms, st)
+                                                             T.f2.map_alt_lo, h->mS_q[0], h->mS_q[1], M, fp, h->num_sms, st)
                             : tc::launch_ffn_fused<1, false>(h->mA_q[0], h->mA_q[0], T.f1.map_alt_hi, T.f1.map_alt_hi, T.f2.map_alt_hi,
-                                                             T.f2.map_alt_hi, M, fp, h->num_sms, st);
+                                                             T.f2.map_alt_hi, h->mS_q[0], h->mS_q[0], M, fp, h->num_sms, st);
                 prof_end(h, st);
                 if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "fused ffn setup failed: %s", cudaGetErrorString(e_));
                 LAUNCH_CHECK(h);

@@ -31,6 +31,7 @@ struct FfnParams {
     SplitOut split;          // planes of the new q
     float* out;              // optional fp32 copy [M][256]
     unsigned long long* dbg; // optional [8] cycle counters of the MMA issuer (profiling aid)
+    int tma_stores;          // 1: the new q planes leave through TMA box stores (mapOhi / mapOlo) from the staging tiles
 };
 
 constexpr int kFfnThreads = 32 * 18;
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_constant__ CUtensorMap mapA1lo,
                  const __grid_constant__ CUtensorMap mapW1hi, const __grid_constant__ CUtensorMap mapW1lo,
                  const __grid_constant__ CUtensorMap mapW2hi, const __grid_constant__ CUtensorMap mapW2lo,
+                 const __grid_constant__ CUtensorMap mapOhi, const __grid_constant__ CUtensorMap mapOlo,
                  int M, FfnParams p) {
     constexpr int kChunks = kFFN / 128;                 // 8
     constexpr int kPl = NSPLIT > 1 ? 2 : 1;             // planes per operand
@@ -471,11 +473,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                             l2[i] = __floats2half2_rn(a - back.x, bq - back.y);
                         }
                     }
-                    const size_t o = (size_t)wrow0 * p.split.ld + col + sub * 16;
-                    stage_store_32b(stg, hi, p.split.hi + o, p.split.ld, rows_valid, lane);
-                    if (NSPLIT > 1) stage_store_32b(stg, lo, p.split.lo + o, p.split.ld, rows_valid, lane);
+                    if (p.tma_stores) {      // one TMA box store per 32 x 32-byte piece instead of LDS + STG by every thread
+                        stage_tma_store_32(stg, hi, &mapOhi, col + sub * 16, wrow0, lane);
+                        if (NSPLIT > 1) stage_tma_store_32(stg, lo, &mapOlo, col + sub * 16, wrow0, lane);
+                    } else {
+                        const size_t o = (size_t)wrow0 * p.split.ld + col + sub * 16;
+                        stage_store_32b(stg, hi, p.split.hi + o, p.split.ld, rows_valid, lane);
+                        if (NSPLIT > 1) stage_store_32b(stg, lo, p.split.lo + o, p.split.ld, rows_valid, lane);
+                    }
                 }
                 if (p.out) {                                 // fp32 copy for test taps: 8 columns (32-byte rows) at a time
+                    if (p.tma_stores) stage_tma_sync(lane);
 #pragma unroll
                     for (int s8 = 0; s8 < 4; ++s8)
                         stage_store_32b(stg, reinterpret_cast<const uint4*>(&v[s8 * 8]),
@@ -485,8 +493,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) arrive(d2_empty);
-            named_bar_sync(1 + q, 128);                  // partners may reuse this warp's tile for the next tile's partials
+            if (p.tma_stores) stage_tma_sync(lane);      // the TMA unit has read this warp's tile ...
+            named_bar_sync(1 + q, 128);                  // ... before partners reuse it for the next tile's partials
         }
+        if (p.tma_stores && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -499,7 +509,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
 
 template <int NSPLIT, bool PAIR, bool DBG>
 inline cudaError_t launch_ffn_fused_(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
-                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
+                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo,
+                                    const CUtensorMap& oHi, const CUtensorMap& oLo, int M,
                                     const FfnParams& p, int num_sms, cudaStream_t st) {
     auto kern = ffn_fused_kernel<NSPLIT, PAIR, DBG>;
     {   // per-device attribute
@@ -515,7 +526,7 @@ inline cudaError_t launch_ffn_fused_(const CUtensorMap& a1Hi, const CUtensorMap&
     if (!PAIR) {
         const int n_tiles = (M + BM - 1) / BM;
         const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-        kern<<<grid, kFfnThreads, kFfnSmem, st>>>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
+        kern<<<grid, kFfnThreads, kFfnSmem, st>>>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, oHi, oLo, M, p);
         return cudaGetLastError();
     }
     const int n_rounds = (M + 2 * BM - 1) / (2 * BM);
@@ -530,15 +541,16 @@ inline cudaError_t launch_ffn_fused_(const CUtensorMap& a1Hi, const CUtensorMap&
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p);
+    return cudaLaunchKernelEx(&cfg, kern, a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, oHi, oLo, M, p);
 }
 
 template <int NSPLIT, bool PAIR>
 inline cudaError_t launch_ffn_fused(const CUtensorMap& a1Hi, const CUtensorMap& a1Lo, const CUtensorMap& w1Hi,
-                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo, int M,
+                                    const CUtensorMap& w1Lo, const CUtensorMap& w2Hi, const CUtensorMap& w2Lo,
+                                    const CUtensorMap& oHi, const CUtensorMap& oLo, int M,
                                     const FfnParams& p, int num_sms, cudaStream_t st) {
-    return p.dbg ? launch_ffn_fused_<NSPLIT, PAIR, true>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p, num_sms, st)
-                 : launch_ffn_fused_<NSPLIT, PAIR, false>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, M, p, num_sms, st);
+    return p.dbg ? launch_ffn_fused_<NSPLIT, PAIR, true>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, oHi, oLo, M, p, num_sms, st)
+                 : launch_ffn_fused_<NSPLIT, PAIR, false>(a1Hi, a1Lo, w1Hi, w1Lo, w2Hi, w2Lo, oHi, oLo, M, p, num_sms, st);
 }
 
 }  // namespace tc
