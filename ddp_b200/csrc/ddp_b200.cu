@@ -74,6 +74,7 @@ struct ddp_handle {
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
     bool qproj_fused = false;   // value + sampling projections in one kernel (qproj_fused.cuh), DDP_B200_QPROJ_FUSED
+    bool gemm_tma_stores = true;    // DDP_B200_GEMM_TMA_STORES: out_proj / head_in write their q planes through TMA box stores
     bool ffn_tma_stores = true;     // DDP_B200_FFN_TMA_STORES: the fused FFN's new q planes leave through TMA box stores
     bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
     int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
@@ -87,9 +88,10 @@ struct ddp_handle {
     int out_bn = 32;
     // activation TMA maps of the ACTIVE batch slice (copied from the cache below by ensure_activation_maps)
     CUtensorMap mA_state[2], mA_q[2], mA_g[2], mA_hid[2];
-    CUtensorMap mS_q[2];                // TMA STORE maps of the q planes (fused FFN epilogue)
+    CUtensorMap mS_q[2];                // TMA STORE maps of the q planes (fused FFN epilogue: 32-byte boxes)
+    CUtensorMap mS_q128[2];             // ... with 128-byte boxes (out_proj / head_in epilogues of gemm_tc_kernel)
     CUtensorMap mS_V, mS_rec;           // TMA STORE maps of the value tensor and the sampling records (qproj_fused epilogue)
-    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2], vout, rec, qs[2]; };
+    struct ActMaps { const void* ws; int b0, nb; CUtensorMap state[2], q[2], g[2], hid[2], vout, rec, qs[2], qs128[2]; };
     std::vector<ActMaps> map_cache;     // one entry per (workspace, first image, image count) a call has used since ddp_plan
     int cur_B = 0, cur_rows = 0;        // images / rows of the slice the launches below work on (== B, rows unless ddp_sample_host chunks)
 
@@ -344,8 +346,8 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
     do {                                                                                                              \
         prof_begin(h, tag, st);                                                                                       \
         cudaError_t e_ = (h)->nsplit == 3                                                                             \
-            ? tc::launch_gemm_tc<BN_, 3, EPI_>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_hi, (W).map_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st) \
-            : tc::launch_gemm_tc<BN_, 1, EPI_>((aMaps)[0], (aMaps)[0], (a2Maps)[0], (a2Maps)[0], (W).map_hi, (W).map_hi, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st); \
+            ? tc::launch_gemm_tc<BN_, 3, EPI_>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_hi, (W).map_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st, &(h)->mS_q128[0], &(h)->mS_q128[1]) \
+            : tc::launch_gemm_tc<BN_, 1, EPI_>((aMaps)[0], (aMaps)[0], (a2Maps)[0], (a2Maps)[0], (W).map_hi, (W).map_hi, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st, &(h)->mS_q128[0], &(h)->mS_q128[0]); \
         prof_end(h, st);                                                                                              \
         if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "tcgen05 gemm setup failed: %s", cudaGetErrorString(e_));  \
         LAUNCH_CHECK(h);                                                                                              \
@@ -360,8 +362,8 @@ inline void prof_end(ddp_handle* h, cudaStream_t st) {
         if (!((h)->gemm_pair & (bit))) { TC_GEMM2(h, tag, st, BN_, EPI_, aMaps, a2Maps, K1_, W, M_, ncols_pad, ep); break; }    \
         prof_begin(h, tag, st);                                                                                       \
         cudaError_t e_ = (h)->nsplit == 3                                                                             \
-            ? tc::launch_gemm_tc<BN_, 3, EPI_, true>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_pair_hi, (W).map_pair_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st) \
-            : tc::launch_gemm_tc<BN_, 1, EPI_, true>((aMaps)[0], (aMaps)[0], (a2Maps)[0], (a2Maps)[0], (W).map_pair_hi, (W).map_pair_hi, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st); \
+            ? tc::launch_gemm_tc<BN_, 3, EPI_, true>((aMaps)[0], (aMaps)[1], (a2Maps)[0], (a2Maps)[1], (W).map_pair_hi, (W).map_pair_lo, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st, &(h)->mS_q128[0], &(h)->mS_q128[1]) \
+            : tc::launch_gemm_tc<BN_, 1, EPI_, true>((aMaps)[0], (aMaps)[0], (a2Maps)[0], (a2Maps)[0], (W).map_pair_hi, (W).map_pair_hi, M_, (W).K, K1_, ncols_pad, ep, (h)->num_sms, st, &(h)->mS_q128[0], &(h)->mS_q128[0]); \
         prof_end(h, st);                                                                                              \
         if (e_ != cudaSuccess) return fail(h, DDP_ERR_CUDA, "tcgen05 pair gemm setup failed: %s", cudaGetErrorString(e_)); \
         LAUNCH_CHECK(h);                                                                                              \
@@ -602,7 +604,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     auto activate = [&](const ddp_handle::ActMaps& a) {
         memcpy(h->mA_state, a.state, sizeof(a.state)); memcpy(h->mA_q, a.q, sizeof(a.q));
         memcpy(h->mA_g, a.g, sizeof(a.g)); memcpy(h->mA_hid, a.hid, sizeof(a.hid));
-        h->mS_V = a.vout; h->mS_rec = a.rec; h->mS_q[0] = a.qs[0]; h->mS_q[1] = a.qs[1];
+        h->mS_V = a.vout; h->mS_rec = a.rec; h->mS_q[0] = a.qs[0]; h->mS_q[1] = a.qs[1]; h->mS_q128[0] = a.qs128[0]; h->mS_q128[1] = a.qs128[1];
     };
     for (const auto& a : h->map_cache)
         if (a.ws == ws_base && a.b0 == b0 && a.nb == nb) { activate(a); return DDP_OK; }
@@ -619,6 +621,7 @@ int ensure_activation_maps(ddp_handle* h, const void* ws_base, const Workspace& 
     ok = ok && tc::make_map_f16(&a.hid[0], ws.hid_hi, M, kFFN, tc::BM) && tc::make_map_f16(&a.hid[1], ws.hid_lo, M, kFFN, tc::BM);
     ok = ok && tc::make_store_map_32bit(&a.vout, ws.V, M, kE, 16, true) && tc::make_store_map_32bit(&a.rec, ws.rec, M, kRecW, 8, false);
     ok = ok && tc::make_store_map_f16_32B(&a.qs[0], ws.q_hi, M, kE) && tc::make_store_map_f16_32B(&a.qs[1], ws.q_lo, M, kE);
+    ok = ok && tc::make_store_map_f16_128B(&a.qs128[0], ws.q_hi, M, kE) && tc::make_store_map_f16_128B(&a.qs128[1], ws.q_lo, M, kE);
     if (!ok) return fail(h, DDP_ERR_CUDA, "cuTensorMapEncodeTiled failed for an activation plane");
     h->map_cache.push_back(a);
     activate(a);
@@ -685,6 +688,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* gs = getenv("DDP_B200_GEMM_TMA_STORES");
+        h->gemm_tma_stores = gs == nullptr || atoi(gs) != 0;            // default on; 0 = per-thread staged stores
         const char* fs = getenv("DDP_B200_FFN_TMA_STORES");
         h->ffn_tma_stores = fs == nullptr || atoi(fs) != 0;             // default on; 0 = per-thread staged stores
         const char* ts = getenv("DDP_B200_QPROJ_TMA_STORES");
@@ -1043,6 +1048,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 ep.scale = T.o.inv_scale; ep.bias = L.bo; ep.out = has_tap(h, DDP_TAP_LN1, k, j) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
                 ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
                 ep.ln_g = L.g1; ep.ln_b = L.e1;
+                ep.tma_stores = h->gemm_tma_stores ? 1 : 0;
                 TC_GEMM2P(4, h, DDP_K_OUT_PROJ, st, 256, tc::EPI_RES_LN, h->mA_g, h->mA_q, kE, T.o, M, kE, ep);      // [g | q] x [Wo | I]
             }
             if ((rc = do_tap(h, DDP_TAP_LN1, k, j, ws.q, (size_t)M * kE, st))) return rc;
@@ -1300,6 +1306,7 @@ static int sample_slice(ddp_handle* h, const float* x, const float* noise, float
             ep.scale = h->tc_in.inv_scale; ep.out = has_tap(h, DDP_TAP_HEAD_IN, k, -1) ? ws.q : nullptr; ep.ldc = kE; ep.ncols = kE;
             ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
             ep.cond = ws.cond; ep.N_tok = N; ep.R = R;
+            ep.tma_stores = h->gemm_tma_stores ? 1 : 0;
             TC_GEMM(h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, h->mA_state, h->tc_in, M, kE, ep);
         } else if (seg) {
             EpiAddCond epi{ws.q, ws.cond, N, R, M};

@@ -335,9 +335,22 @@ __device__ __forceinline__ void stage_store_f16_32(float* stg, const uint4* h, _
     __syncwarp();
 }
 // fp16 planes of kActScale * v[0..63]; lo plane skipped when NSPLIT == 1
+// 32 rows x 128 bytes (one 64-column fp16 plane block) through the warp's 4 KB tile and ONE TMA box store: the XOR pattern
+// of stage_store_f16 is the SWIZZLE_128B layout; map: box {64 halves, 32 rows}
+__device__ __forceinline__ void stage_tma_store_128(float* stg, const uint4* h, const CUtensorMap* map, int c0, int row0, int lane) {
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+    uint4* s16 = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s16[lane * 8 + (j ^ (lane & 7))] = h[j];
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) tma_store_2d(map, stg, c0, row0);
+}
 template <int NSPLIT>
 __device__ __forceinline__ void split_store64(float* stg, const float (&v)[64], const SplitOut& o, size_t row0, int col,
-                                              int rows_valid, int lane) {
+                                              int rows_valid, int lane, const CUtensorMap* mhi = nullptr,
+                                              const CUtensorMap* mlo = nullptr) {
     uint4 hi[8], lo[8];
     __half2* h2 = reinterpret_cast<__half2*>(hi);
     __half2* l2 = reinterpret_cast<__half2*>(lo);
@@ -350,6 +363,11 @@ __device__ __forceinline__ void split_store64(float* stg, const float (&v)[64], 
             const float2 back = __half22float2(hh);
             l2[i] = __floats2half2_rn(a - back.x, b - back.y);
         }
+    }
+    if (mhi) {
+        stage_tma_store_128(stg, hi, mhi, col, (int)row0, lane);
+        if (NSPLIT > 1) stage_tma_store_128(stg, lo, mlo, col, (int)row0, lane);
+        return;
     }
     stage_store_f16(stg, hi, o.hi + row0 * o.ld + col, o.ld, rows_valid, lane);
     if (NSPLIT > 1) stage_store_f16(stg, lo, o.lo + row0 * o.ld + col, o.ld, rows_valid, lane);
@@ -446,6 +464,9 @@ struct EpiParams {
     // coordinate: the zero border supplies the padding and keeps shifts from wrapping into the neighbouring row / image,
     // rows outside the tensor are zero-filled by TMA.  0 = ordinary GEMM.
     int conv_pitch;
+    // 1: the fp16 output planes (split) leave through TMA box stores (kernel parameters mapOhi / mapOlo: the planes with
+    // {64 halves, 32 rows} boxes, SWIZZLE_128B) instead of LDS + STG by every thread.  EPI_RES_LN / EPI_ADD_COND / EPI_BIAS.
+    int tma_stores;
 };
 
 // Sampling-projection epilogue of ONE warp.  Accumulator columns at t_row: 0..63 = (x, y) offsets of 32 sampling points
@@ -554,6 +575,7 @@ __global__ void __launch_bounds__(tc_threads(EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapA2hi, const __grid_constant__ CUtensorMap mapA2lo,
                const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ CUtensorMap mapOhi, const __grid_constant__ CUtensorMap mapOlo,
                int M, int K, int K1, int n_tiles_n, EpiParams ep) {
     // A is the K-concatenation [A (K1 columns) | A2 (K - K1 columns)]: the residual of a post-norm block rides
     // along as extra K against a scaled identity block of W, so the epilogue never reads it from global memory.
@@ -770,13 +792,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         v[i * 4 + 3] = fmaf((v[i * 4 + 3] - mean) * rstd, g4.w, b4.w);
                     }
                     if (ep.out) {                     // fp32 copy only when someone reads it (tests tap it); the planes carry the data
+                        if (ep.tma_stores) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
                         float* dst = ep.out + (size_t)wrow0 * ep.ldc + c;
                         stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
                         stage_store_f32(stg, &v[32], dst + 32, ep.ldc, rows_valid, lane);
                     }
-                    if (ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, c, rows_valid, lane);
+                    if (ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, c, rows_valid, lane,
+                                                           ep.tma_stores ? &mapOhi : nullptr, ep.tma_stores ? &mapOlo : nullptr);
                 }
-                named_bar_sync(1 + q, 64);        // the partner may write the next tile's partials into this tile only now
+                if (ep.tma_stores) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }     // the TMA unit has read this tile ...
+                named_bar_sync(1 + q, 64);        // ... and the partner may write the next tile's partials into it only now
             } else if (EPI == EPI_GELU) {
                 // 16 warps x 64 columns, in two 32-column rounds; everything in the 16x-scaled domain of the fp16 planes:
                 // z16 = 16 (acc*scale + bias); planes of gelu(z) * 16 = z16 * Phi(z16 / 16)
@@ -855,6 +880,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                         }
                     }
                     if (ep.out) {
+                        if (ep.tma_stores) { if (lane == 0) tma_store_wait_read(); __syncwarp(); }
                         if ((ep.ldc & 3) == 0 && col0 + 32 <= ep.ncols) {
                             float* dst = ep.out + (size_t)wrow0 * ep.ldc + col0;
                             stage_store_f32(stg, &v[0], dst, ep.ldc, rows_valid, lane);
@@ -865,7 +891,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
                                 if (col0 + i < ep.ncols) ep.out[(size_t)row * ep.ldc + col0 + i] = v[i];
                         }
                     }
-                    if (W == 64 && ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, col0, rows_valid, lane);
+                    if (W == 64 && ep.split.hi) split_store64<NSPLIT>(stg, v, ep.split, (size_t)wrow0, col0, rows_valid, lane,
+                                                                      ep.tma_stores ? &mapOhi : nullptr, ep.tma_stores ? &mapOlo : nullptr);
                 }
             }
             // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -874,6 +901,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant
             if (lane == 0) { if (PAIR) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (ep.tma_stores && lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -930,6 +958,17 @@ inline bool make_store_map_32bit(CUtensorMap* map, const void* base, uint64_t ro
               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp16 plane [rows][cols] for TMA box STORES of 32 rows x 128 bytes (64 halves), SWIZZLE_128B
+inline bool make_store_map_f16_128B(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 // fp16 plane [rows][cols] for TMA box STORES of 32 rows x 32 bytes (16 halves), SWIZZLE_32B
 inline bool make_store_map_f16_32B(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols) {
     PFN_encodeTiled fn = get_encode_fn();
@@ -945,8 +984,11 @@ inline bool make_store_map_f16_32B(CUtensorMap* map, const void* base, uint64_t 
 template <int BN, int NSPLIT, int EPI, bool PAIR = false>
 inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo, const CUtensorMap& a2Hi,
                                   const CUtensorMap& a2Lo, const CUtensorMap& bHi, const CUtensorMap& bLo, int M, int K,
-                                  int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st) {
-    // PAIR: bHi / bLo must be maps with BN / 2-row boxes
+                                  int K1, int n_cols_padded, const EpiParams& ep, int num_sms, cudaStream_t st,
+                                  const CUtensorMap* oHi = nullptr, const CUtensorMap* oLo = nullptr) {
+    // PAIR: bHi / bLo must be maps with BN / 2-row boxes; oHi / oLo (with ep.tma_stores): store maps of the output planes
+    const CUtensorMap& mOh = oHi ? *oHi : bHi;
+    const CUtensorMap& mOl = oLo ? *oLo : bHi;
     using C = Cfg<BN, NSPLIT, EPI, PAIR>;
     auto kern = gemm_tc_kernel<BN, NSPLIT, EPI, PAIR>;
     {   // the attribute is per device: remember it per device ordinal (one handle per GPU, but several GPUs per process are legal)
@@ -964,7 +1006,7 @@ inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo
     if (!PAIR) {
         const int n_tiles = n_tiles_m * n_tiles_n;
         const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-        kern<<<grid, tc_threads(EPI), C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
+        kern<<<grid, tc_threads(EPI), C::kSmemBytes, st>>>(aHi, aLo, a2Hi, a2Lo, bHi, bLo, mOh, mOl, M, K, K1, n_tiles_n, ep);
         return cudaSuccess;
     }
     const int n_rounds = ((n_tiles_m + 1) / 2) * n_tiles_n;
@@ -979,7 +1021,7 @@ inline cudaError_t launch_gemm_tc(const CUtensorMap& aHi, const CUtensorMap& aLo
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, aHi, aLo, a2Hi, a2Lo, bHi, bLo, M, K, K1, n_tiles_n, ep);
+    return cudaLaunchKernelEx(&cfg, kern, aHi, aLo, a2Hi, a2Lo, bHi, bLo, mOh, mOl, M, K, K1, n_tiles_n, ep);
 }
 
 }  // namespace tc
