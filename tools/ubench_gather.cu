@@ -341,6 +341,35 @@ k_gather_tiled(const float* __restrict__ V, const uint32_t* __restrict__ rec, __
     }
 }
 
+// v5: ONE 1024-thread CTA per SM (32 warps = the residency of the product kernel, 64 registers), walking TX x TY = 32-token
+// tiles in row-major tile order, one token per warp, head group 0 for the whole tile, barrier, head group 1.  The four
+// resident CTAs of the product kernel sit on four unrelated image rows (CTAs are dealt round-robin over the SMs), so an
+// SM's L1 sees four 11-row neighbourhoods at once (57 % hits); here it sees ONE (TY + 10) x (TX + 10) neighbourhood of
+// half the heads at a time (~126 KB for 8 x 4).
+template <int TX, int TY, bool GROUP_MAJOR>
+__global__ void __launch_bounds__(1024, 1)
+k_gather_patch(const float* __restrict__ V, const uint32_t* __restrict__ rec, __half* out_hi, __half* out_lo, int H, int W, int rows) {
+    static_assert(TX * TY == 32, "one token per warp");
+    const int N = H * W, tiles_x = (W + TX - 1) / TX, tiles_y = (H + TY - 1) / TY, n_tiles = rows * tiles_x * tiles_y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = (long long)blockIdx.x * n_tiles / gridDim.x, t1 = (long long)(blockIdx.x + 1) * n_tiles / gridDim.x;
+    for (int t = (int)t0; t < (int)t1; ++t) {
+        const int row = t / (tiles_x * tiles_y), r = t - row * tiles_x * tiles_y;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int i = ty * TY + warp / TX, j = tx * TX + warp % TX;
+        const bool ok = i < H && j < W;
+        const int token = row * N + i * W + j;
+        if (GROUP_MAJOR) {
+            if (ok) gather_group(V, rec, out_hi, out_lo, N, W, token, 0, lane);
+            __syncthreads();
+            if (ok) gather_group(V, rec, out_hi, out_lo, N, W, token, 1, lane);
+            __syncthreads();
+        } else {
+            if (ok) { gather_group(V, rec, out_hi, out_lo, N, W, token, 0, lane); gather_group(V, rec, out_hi, out_lo, N, W, token, 1, lane); }
+        }
+    }
+}
+
 // sampling records as the sampling projection's epilogue writes them, from synthetic offsets
 __global__ void k_make_records(uint32_t* rec, int H, int W, int total, float sigma, uint32_t seed) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head * 4 + point)
@@ -470,6 +499,25 @@ int main(int argc, char** argv) {
         run4("v4 TMA 16x8 win 24x16 x4 512t", k_gather_smem<16, 8, 24, 16, 4, 512>, 24, 16, 4, 512);
         run4("v4 TMA 32x8 win 40x16 x2 1024t", k_gather_smem<32, 8, 40, 16, 2, 1024>, 40, 16, 2, 1024);
         run4("v4 TMA 16x16 win 28x28 x2 1024t", k_gather_smem<16, 16, 28, 28, 2, 1024>, 28, 28, 2, 1024);
+    }
+    {
+        auto run5 = [&](const char* name, auto kern) {
+            cudaMemset(hi1, 0, (size_t)total * kE * 2);
+            auto l = [&]() { kern<<<sms, 1024>>>(V, rec, hi1, lo1, H, W, rows); };
+            const float ms = time_ms(l, 20);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaMemcpy(got.data(), hi1, got.size() * 2, cudaMemcpyDeviceToHost);
+            size_t bad = 0;
+            for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+            printf("               %-32s 1 CTA/SM   %.3f ms  (%.2fx of v0)  %s%s\n", name, ms, ms0 / ms,
+                   bad ? "OUTPUT DIFFERS " : "bit-identical ", e == cudaSuccess ? "" : cudaGetErrorString(e));
+            if (bad || e != cudaSuccess) rc = 2;
+        };
+        run5("v5 patch 8x4, head-group major", k_gather_patch<8, 4, true>);
+        run5("v5 patch 8x4, token major", k_gather_patch<8, 4, false>);
+        run5("v5 patch 16x2, head-group major", k_gather_patch<16, 2, true>);
+        run5("v5 patch 4x8, head-group major", k_gather_patch<4, 8, true>);
+        run5("v5 patch 32x1, head-group major", k_gather_patch<32, 1, true>);
     }
     run("v1 persistent, row-major tiles", k_gather_tiled<false, false>);
     run("v2 persistent, Z-order tiles", k_gather_tiled<true, false>);
