@@ -32,7 +32,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-template <int TX, int TY, int PW, int PH, int NBUF, int THREADS>
+template <int TX, int TY, int PW, int PH, int NBUF, int THREADS, int PPB = 4>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gather_smem(const __grid_constant__ CUtensorMap mapV, const float* __restrict__ V, const uint32_t* __restrict__ rec,
               __half* out_hi, __half* out_lo, int H, int W, int rows) {
@@ -118,7 +118,9 @@ k_gather_smem(const __grid_constant__ CUtensorMap mapV, const float* __restrict_
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 float4 vv[kPoints][4];
 #pragma unroll
-                for (int p = 0; p < kPoints; ++p) {
+                for (int pb = 0; pb < kPoints; pb += PPB) {      // PPB points' corner loads in flight at a time
+#pragma unroll
+                for (int p = pb; p < pb + PPB; ++p) {
                     const uint32_t wv = w4[p];
                     const int base = (int)(wv & 0x03FFFFFFu);
                     const int dx = (int)((wv >> 26) & 1u);
@@ -142,7 +144,7 @@ k_gather_smem(const __grid_constant__ CUtensorMap mapV, const float* __restrict_
                     }
                 }
 #pragma unroll
-                for (int p = 0; p < kPoints; ++p) {
+                for (int p = pb; p < pb + PPB; ++p) {
                     const uint32_t wv = w4[p];
                     const float wx1 = fx4[p], wy1 = fy4[p], wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
                     const float c00 = (wv & (1u << 28)) ? wy0 * wx0 : 0.f;
@@ -156,6 +158,7 @@ k_gather_smem(const __grid_constant__ CUtensorMap mapV, const float* __restrict_
                     s0 = fmaf(c11, v11.x, s0); s1 = fmaf(c11, v11.y, s1); s2 = fmaf(c11, v11.z, s2); s3 = fmaf(c11, v11.w, s3);
                     acc[0] = fmaf(a4[p], s0, acc[0]); acc[1] = fmaf(a4[p], s1, acc[1]);
                     acc[2] = fmaf(a4[p], s2, acc[2]); acc[3] = fmaf(a4[p], s3, acc[3]);
+                }
                 }
                 const size_t o = (size_t)token * kE + ch;
                 const float a0 = acc[0] * kSplitScale, a1 = acc[1] * kSplitScale, a2 = acc[2] * kSplitScale, a3 = acc[3] * kSplitScale;
@@ -370,6 +373,43 @@ k_gather_patch(const float* __restrict__ V, const uint32_t* __restrict__ rec, __
     }
 }
 
+// v6: the product kernel's geometry (warp = token, 256 threads) with register-free L1 prefetches: the SASS of the product
+// kernel runs six dependent memory round trips per token (records, two batches of 8 corner loads, store; twice) because
+// 64 registers hold only 8 corner loads at a time.  Here the corner lines of head group 1 (MODE & 1) and of the second
+// batch of head group 0 (MODE & 2) are prefetched into L1 (prefetch.global.L1, no destination register) while head group
+// 0's first batch is in flight.
+__device__ __forceinline__ void pf_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+k_gather_pf(const float* __restrict__ V, const uint32_t* __restrict__ rec, __half* out_hi, __half* out_lo, int N, int W, int total_tokens) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= total_tokens) return;
+    int lane = threadIdx.x & 31;
+    int row = warp / N;
+    const uint32_t* rp = rec + (size_t)warp * kRecW;
+    auto prefetch_group = [&](int hg, int p0, int p1) {
+        const int m = hg * 4 + (lane >> 3);
+        const float* Vr = V + (size_t)row * N * kE + m * kHeadDim + (lane & 7) * 4;
+        const uint4 wd = *reinterpret_cast<const uint4*>(rp + m * 4);
+        const uint32_t w4[4] = {wd.x, wd.y, wd.z, wd.w};
+#pragma unroll
+        for (int p = p0; p < p1; ++p) {
+            const uint32_t wv = w4[p];
+            const int base = (int)(wv & 0x03FFFFFFu);
+            const int dx = (int)((wv >> 26) & 1u);
+            const int dy = ((wv >> 27) & 1u) ? W : 0;
+            if ((lane & 7) == 0) {      // one lane per 128-byte line
+                pf_l1(Vr + (size_t)base * kE); pf_l1(Vr + (size_t)(base + dx) * kE);
+                pf_l1(Vr + (size_t)(base + dy) * kE); pf_l1(Vr + (size_t)(base + dy + dx) * kE);
+            }
+        }
+    };
+    if (MODE & 2) prefetch_group(0, 2, 4);
+    if (MODE & 1) prefetch_group(1, 0, 4);
+    gather_group(V, rec, out_hi, out_lo, N, W, warp, 0, lane);
+    gather_group(V, rec, out_hi, out_lo, N, W, warp, 1, lane);
+}
+
 // sampling records as the sampling projection's epilogue writes them, from synthetic offsets
 __global__ void k_make_records(uint32_t* rec, int H, int W, int total, float sigma, uint32_t seed) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head * 4 + point)
@@ -499,6 +539,10 @@ int main(int argc, char** argv) {
         run4("v4 TMA 16x8 win 24x16 x4 512t", k_gather_smem<16, 8, 24, 16, 4, 512>, 24, 16, 4, 512);
         run4("v4 TMA 32x8 win 40x16 x2 1024t", k_gather_smem<32, 8, 40, 16, 2, 1024>, 40, 16, 2, 1024);
         run4("v4 TMA 16x16 win 28x28 x2 1024t", k_gather_smem<16, 16, 28, 28, 2, 1024>, 28, 28, 2, 1024);
+        run4("v4b 16x16 win 24x24 x2 1024t 2pt", k_gather_smem<16, 16, 24, 24, 2, 1024, 2>, 24, 24, 2, 1024);
+        run4("v4b 16x16 win 24x24 x3 1024t 2pt", k_gather_smem<16, 16, 24, 24, 3, 1024, 2>, 24, 24, 3, 1024);
+        run4("v4b 16x16 win 24x24 x2 1024t 1pt", k_gather_smem<16, 16, 24, 24, 2, 1024, 1>, 24, 24, 2, 1024);
+        run4("v4b 16x16 win 24x24 x2 512t 2pt", k_gather_smem<16, 16, 24, 24, 2, 512, 2>, 24, 24, 2, 512);
     }
     {
         auto run5 = [&](const char* name, auto kern) {
@@ -518,6 +562,24 @@ int main(int argc, char** argv) {
         run5("v5 patch 16x2, head-group major", k_gather_patch<16, 2, true>);
         run5("v5 patch 4x8, head-group major", k_gather_patch<4, 8, true>);
         run5("v5 patch 32x1, head-group major", k_gather_patch<32, 1, true>);
+    }
+    {
+        auto run6 = [&](const char* name, auto kern) {
+            cudaMemset(hi1, 0, (size_t)total * kE * 2);
+            auto l = [&]() { kern<<<(unsigned)(((size_t)total * 32 + 255) / 256), 256>>>(V, rec, hi1, lo1, N, W, total); };
+            const float ms = time_ms(l, 20);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaMemcpy(got.data(), hi1, got.size() * 2, cudaMemcpyDeviceToHost);
+            size_t bad = 0;
+            for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+            printf("               %-32s            %.3f ms  (%.2fx of v0)  %s%s\n", name, ms, ms0 / ms,
+                   bad ? "OUTPUT DIFFERS " : "bit-identical ", e == cudaSuccess ? "" : cudaGetErrorString(e));
+            if (bad || e != cudaSuccess) rc = 2;
+        };
+        run6("v6 no prefetch (gather_group x2)", k_gather_pf<0>);
+        run6("v6 L1 prefetch of head group 1", k_gather_pf<1>);
+        run6("v6 L1 prefetch hg0 batch 2", k_gather_pf<2>);
+        run6("v6 L1 prefetch both", k_gather_pf<3>);
     }
     run("v1 persistent, row-major tiles", k_gather_tiled<false, false>);
     run("v2 persistent, Z-order tiles", k_gather_tiled<true, false>);
