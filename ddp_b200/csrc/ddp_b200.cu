@@ -83,7 +83,8 @@ struct ddp_handle {
     int nsplit = 1;
     int num_sms = 148;
     __half* tc_arena = nullptr;
-    TcWeight tc_in, tc_out;
+    TcWeight tc_in, tc_out, tc_cond;   // tc_cond: the x half of transform / down (cond = W_x x + b, once per call)
+    bool cond_tc = true;                // DDP_B200_COND_TC: that GEMM on tcgen05 (tc_3xf16) instead of the fp32 CUDA-core GEMM
     TcLayer tcL[kMaxLayers];
     int out_bn = 32;
     // activation TMA maps of the ACTIVE batch slice (copied from the cache below by ensure_activation_maps)
@@ -456,6 +457,7 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
     size_t halves = 0;
     auto need = [&](int rows_pad, int K) { halves += 2 * (size_t)rows_pad * K; };
     need(kE, kE);
+    need(kE, kE);      // tc_cond
     for (int j = 0; j < Lc; ++j) { need(kE, kE); need(128, kE); need(kE, 2 * kE); need(kFFN, kE); need(kE, kFFN + kE); }
     need(h->out_bn, kE);
     if (h->tc_arena) { cudaFree(h->tc_arena); h->tc_arena = nullptr; }
@@ -467,6 +469,11 @@ int commit_tc_weights(ddp_handle* h, cudaStream_t st) {
     if (seg) {
         WeightSpec* w = spec("transform.conv.weight");        // (256, 512): the mask half is columns 256..511
         if ((rc = make_tc_weight(h, h->tc_in, cur, kE, kE, 256, {{w->dev, &w->host, kE, 2 * kE, 1, kE, 0}}, st))) return rc;
+        // the x half (columns 0..255).  weight_shift looks at the whole host tensor: a common shift for both halves is fine
+        if ((rc = make_tc_weight(h, h->tc_cond, cur, kE, kE, 256, {{w->dev, &w->host, kE, 2 * kE, 1, 0, 0}}, st))) return rc;
+    } else {
+        WeightSpec* w = spec("down.conv.weight");             // (256, 257): x columns 0..255, the depth channel is column 256
+        if ((rc = make_tc_weight(h, h->tc_cond, cur, kE, kE, 256, {{w->dev, &w->host, kE, kE + 1, 1, 0, 0}}, st))) return rc;
     }
     for (int j = 0; j < Lc; ++j) {
         std::string p = "decode_head.encoder.layers." + std::to_string(j) + ".";
@@ -694,6 +701,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         h->ffn_tma_stores = fs == nullptr || atoi(fs) != 0;             // default on; 0 = per-thread staged stores
         const char* ts = getenv("DDP_B200_QPROJ_TMA_STORES");
         h->qproj_tma_stores = ts == nullptr || atoi(ts) != 0;           // default on; 0 = per-thread staged stores
+        const char* ct = getenv("DDP_B200_COND_TC");
+        h->cond_tc = ct == nullptr || atoi(ct) != 0;                    // default on; 0 = fp32 CUDA-core cond GEMM
         const char* hc = getenv("DDP_B200_HOST_CHUNKS");
         h->host_chunks = hc ? atoi(hc) : 0;                             // ddp_sample_host pipeline depth (0 = automatic)
         const char* gr = getenv("DDP_B200_GRAPH");
@@ -1285,12 +1294,21 @@ static int sample_slice(ddp_handle* h, const float* x, const float* noise, float
     carve(h, workspace, &ws_full, nullptr);
     ws = slice_ws(h, ws_full, b0);
 
+    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws, b0, nb))) return rc;
     // cond = W_x x + b: the step-invariant half of transform / down (x is read once, reused for all T steps)
-    {
+    if (h->tc && h->cond_tc && h->nsplit == 3) {
+        // tensor-core form: x (NCHW) -> token-major fp32 (in q's buffer, free until the first head-in) -> fp16 planes -> GEMM
+        dim3 grid((N + 31) / 32, kE / 32, B), block(32, 8);
+        KLAUNCH(h, DDP_K_COND, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(x, ws.q, kE, N)));
+        const size_t n8 = (size_t)B * N * kE / 8;
+        KLAUNCH(h, DDP_K_COND, st, (k_split_planes<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(ws.q, ws.q_hi, ws.q_lo, n8)));
+        tc::EpiParams ep{};
+        ep.scale = h->tc_cond.inv_scale; ep.bias = h->b_tr; ep.out = ws.cond; ep.ldc = kE; ep.ncols = kE;
+        TC_GEMM(h, DDP_K_COND, st, 256, tc::EPI_BIAS, h->mA_q, h->tc_cond, B * N, kE, ep);
+    } else {
         EpiBias epi{ws.cond, h->b_tr, kE, kE, B * N};
         KLAUNCH(h, DDP_K_COND, st, (launch_gemm_simt<256, true>(x, 0, N, h->Wx_t, kE, B * N, kE, kE, epi, st)));
     }
-    if (h->tc && (rc = ensure_activation_maps(h, workspace, ws, b0, nb))) return rc;
     const bool s3 = h->nsplit == 3;
     if ((rc = load_state(h, noise, ws.state, ws.state_hi, ws.state_lo, st))) return rc;
     if (seg) CUDA_TRY(h, cudaMemsetAsync(ws.accum, 0, (size_t)B * N * C * sizeof(float), st));
