@@ -355,6 +355,37 @@ def test_plugin_ddim_sample_matches_oracle(mode):
     P.check_seg_parity(model.engine(), W, cfg, x, drawn.cpu(), f"plugin ddim_sample, internal noise [{mode}]", ref=ref2, out=out2.cpu())
 
 
+def test_plugin_engine_follows_parameter_changes_by_any_route():
+    """The cached CUDA engine must be rebuilt when parameters change without going through load_state_dict: mmcv's
+    load_checkpoint recurses over _load_from_state_dict, and in-place edits bypass every hook.  The
+    (data_ptr, _version) fingerprint of ddp_b200/_stale.py catches both."""
+    model = _toy_model(timesteps=2)
+    cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=2)
+    W = O.make_weights(cfg, seed=81)
+    model.load_state_dict(W, strict=False)
+    model = model.cuda().eval()
+    x, noise = O.make_inputs(cfg, 1, 8, 10, seed=82)
+    a = model.ddim_sample(x.cuda(), None, noise=noise.cuda())
+    eng = model.engine()
+    assert model.engine() is eng                                   # unchanged parameters: the engine is reused
+    with torch.no_grad():                                          # in-place edit of one hot-path weight
+        model.decode_head.conv_seg.weight.mul_(-1.0)
+    b = model.ddim_sample(x.cuda(), None, noise=noise.cuda())
+    assert model.engine() is not eng and not torch.equal(a, b)
+    W2 = dict(W)
+    W2["decode_head.conv_seg.weight"] = -W["decode_head.conv_seg.weight"]
+    ref = O.sample(W2, cfg, x, noise)
+    P.check_seg_parity(model.engine(), W2, cfg, x, noise, "engine after an in-place weight edit", ref=ref, out=b.cpu())
+    # the route mmcv's load_checkpoint takes: per-module _load_from_state_dict, never Module.load_state_dict
+    sd = {k: v.cuda() for k, v in W.items()}
+    with torch.no_grad():
+        for name, mod in model.named_modules():
+            prefix = name + "." if name else ""
+            mod._load_from_state_dict(sd, prefix, {}, False, [], [], [])
+    c = model.ddim_sample(x.cuda(), None, noise=noise.cuda())
+    assert torch.equal(c, a)
+
+
 def test_plugin_simple_test_end_to_end():
     """img -> (toy) encoder -> ddim loop in the library -> x4 bilinear resize -> softmax -> argmax -> numpy,
     i.e. BaseSegmentor.forward(return_loss=False) as tools/test.py calls it."""

@@ -1,10 +1,8 @@
 """GPU parity tests of the BEV map-segmentation variant through the C ABI: against the golden outputs
 of the unmodified reference BEV classes and against the oracle.
 
-STATUS: built after the round-1 GPU budget was spent.  What this variant adds around the (hardware-verified) denoiser is
-checked against the oracle by the host emulation (tests/test_bev_emu_cpu.py); the CUDA build of it has not run on
-hardware yet, hence `first_hw_run` (collected last, non-strict xfail — see tests/conftest.py).  Remove the marker after
-the first green GPU run.
+Round 2: all of these run green on a B200 (the round-1 hardware failures were one Python line in
+BevDecodeEngine.weight_names, profiles/r02_notes.md section 1); compute-sanitizer memcheck clean.
 """
 import os
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # full GPU suite (with parity log) + the default bench run, as the driver runs them
 set -u
-OUT=gpurun_out/r02_hw9
+OUT=gpurun_out/full_check
 mkdir -p "$OUT"
 export DDP_PARITY_LOG=$PWD/$OUT/parity_log.jsonl
 run() { local name=$1; shift; echo "== $name: $*"; timeout "${T:-900}" "$@" > "$OUT/$name.log" 2>&1; echo "   exit $? (log: $OUT/$name.log)"; tail -n ${TAILN:-6} "$OUT/$name.log" | cut -c1-600; }

@@ -2,7 +2,7 @@
 # N-GPU bench exactly as the driver launches it
 set -u
 N=${1:-2}
-OUT=gpurun_out/r02_multi
+OUT=gpurun_out/multi
 mkdir -p "$OUT"
 python __graft_entry__.py > "$OUT/build.log" 2>&1 || { echo "build failed"; tail -n 30 "$OUT/build.log"; exit 1; }
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 5 --warmup 3 > "$OUT/bench_n$N.log" 2>&1
