@@ -74,6 +74,7 @@ struct ddp_handle {
     bool tc = false;
     bool fuse_ffn = false;      // fused FFN1 -> GELU -> FFN2 -> LN kernel (ffn_fused.cuh)
     bool qproj_fused = false;   // value + sampling projections in one kernel (qproj_fused.cuh), DDP_B200_QPROJ_FUSED
+    bool ffn_pull = true;           // DDP_B200_FFN_PULL: chunk 0 of the next tile ahead of the current tile's LayerNorm (ffn_fused.cuh)
     bool gemm_tma_stores = true;    // DDP_B200_GEMM_TMA_STORES: out_proj / head_in write their q planes through TMA box stores
     bool ffn_tma_stores = true;     // DDP_B200_FFN_TMA_STORES: the fused FFN's new q planes leave through TMA box stores
     bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
@@ -695,6 +696,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         const char* pe = getenv("DDP_B200_FFN_PAIR");
         h->ffn_pair = h->fuse_ffn && (pe == nullptr || atoi(pe) != 0);   // default on; 0 = one CTA per 128 tokens
         if (h->num_sms < 2) { h->ffn_pair = false; h->qproj_fused = false; h->gemm_pair = 0; }   // CTA pairs need two SMs
+        const char* fpl = getenv("DDP_B200_FFN_PULL");
+        h->ffn_pull = fpl == nullptr || atoi(fpl) != 0;                 // default on
         const char* gs = getenv("DDP_B200_GEMM_TMA_STORES");
         h->gemm_tma_stores = gs == nullptr || atoi(gs) != 0;            // default on; 0 = per-thread staged stores
         const char* fs = getenv("DDP_B200_FFN_TMA_STORES");
@@ -1069,6 +1072,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 fp.out = has_tap(h, DDP_TAP_LAYER_OUT, k, j) ? ws.q : nullptr;
                 fp.dbg = h->ffn_dbg;
                 fp.tma_stores = h->ffn_tma_stores ? 1 : 0;
+                fp.pull_ahead = h->ffn_pull ? 1 : 0;
                 prof_begin(h, DDP_K_FFN_FUSED, st);
                 cudaError_t e_;
                 if (h->ffn_pair)

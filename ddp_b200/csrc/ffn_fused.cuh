@@ -32,6 +32,10 @@ struct FfnParams {
     float* out;              // optional fp32 copy [M][256]
     unsigned long long* dbg; // optional [8] cycle counters of the MMA issuer (profiling aid)
     int tma_stores;          // 1: the new q planes leave through TMA box stores (mapOhi / mapOlo) from the staging tiles
+    // 1: chunk 0 of the NEXT tile is pulled ahead of the current tile's last MMA2 and LayerNorm: its MMA1 is issued between
+    // MMA2(6) and MMA2(7), its GELU runs while MMA2(7) executes, and only then do the epilogue warps turn to the LayerNorm.
+    // Without it the tensor pipe waits at every tile boundary for LN(t) AND GELU(t+1, 0), which share the same 16 warps.
+    int pull_ahead;
 };
 
 constexpr int kFfnThreads = 32 * 18;
@@ -155,9 +159,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                     for (int nh = 0; nh < 2; ++nh)
                         put(&mapW2hi, nh * 128, NSPLIT > 1 ? &mapW2lo : nullptr, nh * 128, cc * 128 + kb2 * 64);
             };
-            for (int r = round0; r < n_rounds; r += round_step) {
-                const int m0 = row_of(r);
+            auto load_a1 = [&](int m0) {                 // q planes of one tile (waits until the previous tile's MMAs released them)
                 mbar_wait(a1_empty, tphase ^ 1);
+                tphase ^= 1;
                 if (!PAIR || leader) mbar_expect_tx(a1_full, kNCta * kPl * 4 * kFfnUnit);
                 for (int kb = 0; kb < 4; ++kb) {
                     if (PAIR) {
@@ -168,16 +172,26 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         if (NSPLIT > 1) tma_load_2d(a1 + (4 + kb) * kFfnUnit, &mapA1lo, a1_full, kb * BK, m0);
                     }
                 }
+            };
+            auto put_w1 = [&](int c) {                   // W1 rows of hidden chunk c (128 rows), per K block: hi | lo
+                for (int kb = 0; kb < 4; ++kb) put(&mapW1hi, c * 128, NSPLIT > 1 ? &mapW1lo : nullptr, c * 128, kb * BK);
+            };
+            bool pulled = false;                         // this tile's planes + W1 chunk 0 were queued at the end of the previous tile
+            for (int r = round0; r < n_rounds; r += round_step) {
+                if (!pulled) load_a1(row_of(r));
                 for (int c = 0; c < kChunks; ++c) {
-                    for (int kb = 0; kb < 4; ++kb)       // W1 rows of hidden chunk c (128 rows), K block kb: hi | lo
-                        put(&mapW1hi, c * 128, NSPLIT > 1 ? &mapW1lo : nullptr, c * 128, kb * BK);
+                    if (!(c == 0 && pulled)) put_w1(c);
                     if (c == kChunks - 1)                // identity block of the augmented W2 (hi plane only): the residual
                         for (int kb = 0; kb < 4; ++kb)   // is issued right after the last MMA1 (see the MMA warp); unit = both N halves
                             put(&mapW2hi, 0, &mapW2hi, 128, kFFN + kb * BK);
                     if (c >= 1) put_w2(c - 1);
                 }
+                pulled = p.pull_ahead && r + round_step < n_rounds;
+                if (pulled) {                            // the ring is FIFO: same order as the MMA warp consumes (… M2(6), M1'(0), M2(7))
+                    load_a1(row_of(r + round_step));
+                    put_w1(0);
+                }
                 put_w2(kChunks - 1);
-                tphase ^= 1;
             }
         }
         __syncwarp();
@@ -242,39 +256,49 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 if (elect_one()) commit(a2_empty);
                 __syncwarp();
             };
-            for (int r = round0; r < n_rounds; r += round_step) {
-                { long long t0 = now(); wait(a1_full, tphase); tw_a1 += now() - t0; }
+            auto mma1 = [&](int c) {                     // D1 = A1 * W1[c]^T   (N = 128)
+                (void)c;
+                { long long t0 = now(); wait(d1_empty, d1e_phase ^ 1); d1e_phase ^= 1; tw_d1e += now() - t0; }
                 tc_fence_after();
-                for (int c = 0; c <= kChunks; ++c) {
-                    if (c < kChunks) {                   // D1 = A1 * W1[c]^T   (N = 128)
-                        { long long t0 = now(); wait(d1_empty, d1e_phase ^ 1); d1e_phase ^= 1; tw_d1e += now() - t0; }
-                        tc_fence_after();
-                        for (int kb = 0; kb < 4; ++kb) {
-                            const uint32_t uhi = ring_wait();
-                            const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
-                            const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
-                            const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(uhi + kPlaneB);
-                            const long long ti0 = now();
-                            if (elect_one()) {
+                for (int kb = 0; kb < 4; ++kb) {
+                    const uint32_t uhi = ring_wait();
+                    const uint64_t ahi = make_smem_desc(a1_addr + kb * kFfnUnit);
+                    const uint64_t alo = make_smem_desc(a1_addr + (4 + kb) * kFfnUnit);
+                    const uint64_t bhi = make_smem_desc(uhi), blo = make_smem_desc(uhi + kPlaneB);
+                    const long long ti0 = now();
+                    if (elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint32_t acc = (kb | k) != 0;
-                                    if (NSPLIT > 1) {
-                                        mma_ss(tD1, alo + 2 * k, bhi + 2 * k, acc);
-                                        mma_ss(tD1, ahi + 2 * k, blo + 2 * k, 1u);
-                                        mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, 1u);
-                                    } else {
-                                        mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, acc);
-                                    }
-                                }
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (kb | k) != 0;
+                            if (NSPLIT > 1) {
+                                mma_ss(tD1, alo + 2 * k, bhi + 2 * k, acc);
+                                mma_ss(tD1, ahi + 2 * k, blo + 2 * k, 1u);
+                                mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, 1u);
+                            } else {
+                                mma_ss(tD1, ahi + 2 * k, bhi + 2 * k, acc);
                             }
-                            __syncwarp();
-                            tw_i1 += now() - ti0;
-                            ring_release();
                         }
-                        if (elect_one()) commit(d1_full);
-                        __syncwarp();
                     }
+                    __syncwarp();
+                    tw_i1 += now() - ti0;
+                    ring_release();
+                }
+                if (elect_one()) commit(d1_full);
+                __syncwarp();
+            };
+            auto wait_a1 = [&]() {
+                long long t0 = now();
+                wait(a1_full, tphase);
+                tphase ^= 1;
+                tw_a1 += now() - t0;
+                tc_fence_after();
+            };
+            bool pulled = false;                         // MMA1(0) of this tile was already issued at the end of the previous one
+            for (int r = round0; r < n_rounds; r += round_step) {
+                if (!pulled) wait_a1();
+                const bool pull_next = p.pull_ahead && r + round_step < n_rounds;
+                for (int c = 0; c <= kChunks; ++c) {
+                    if (c < kChunks && !(c == 0 && pulled)) mma1(c);
                     if (c == kChunks - 1) {              // last MMA1 issued: add the residual now and release q's planes early
                     // residual: D2 += q * (2^shift I)^T with q's planes still in shared memory
                     for (int kb = 0; kb < 4; ++kb) {
@@ -300,6 +324,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                         if (elect_one()) commit(a1_empty);   // q planes may be overwritten by the next tile's load
                         __syncwarp();
                     }
+                    if (c == kChunks && pull_next) {     // between MMA2(6) and MMA2(7): chunk 0 of the next tile
+                        wait_a1();
+                        mma1(0);
+                    }
                     if (c >= 1) {
                         if (c == 1) {                    // D2 of the previous tile must have been drained
                             { long long t0 = now(); wait(d2_empty, d2e_phase ^ 1); d2e_phase ^= 1; tw_d2e += now() - t0; }
@@ -310,7 +338,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 }
                 if (elect_one()) commit(d2_full);
                 __syncwarp();
-                tphase ^= 1;
+                pulled = pull_next;
             }
             if (DBG && p.dbg && lane == 0) {
                 atomicAdd(&p.dbg[0], (unsigned long long)(now() - t_all));
@@ -334,13 +362,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
         uint32_t d1f_phase = 0, a2e_phase = 0;
         uint32_t d2f_phase = 0;
         auto arrive = [&](uint64_t* bar) { if (PAIR) mbar_arrive_leader(bar); else mbar_arrive(bar); };
-        for (int r = round0; r < n_rounds; r += round_step) {
-            const int m0 = row_of(r);
-            const int wrow0 = m0 + q * 32;
-            const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
-            // ---- per hidden chunk: GELU of this warp's 32 columns, planes back into TMEM ----
-#pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
+        // GELU of this warp's 32 columns of hidden chunk c: D1 -> registers (D1 released at once) -> fp16 hi/lo planes back into TMEM
+        auto gelu_chunk = [&](int c) {
                 mbar_wait(d1_full, d1f_phase); d1f_phase ^= 1;
                 tc_fence_after();
                 float v[32];
@@ -394,7 +417,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap mapA1hi, const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive(a2_full);
-            }
+                    };
+        bool pulled = false;                             // chunk 0 of this tile was processed at the end of the previous tile
+        for (int r = round0; r < n_rounds; r += round_step) {
+            const int m0 = row_of(r);
+            const int wrow0 = m0 + q * 32;
+            const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
+            // ---- per hidden chunk: GELU of this warp's 32 columns, planes back into TMEM ----
+#pragma unroll 1
+            for (int c = pulled ? 1 : 0; c < kChunks; ++c) gelu_chunk(c);
+            // chunk 0 of the NEXT tile before this tile's LayerNorm: its math runs while MMA2(7) executes (FfnParams::pull_ahead)
+            pulled = p.pull_ahead && r + round_step < n_rounds;
+            if (pulled) gelu_chunk(0);
             // ---- final: LayerNorm (+ folded FiLM) of this warp's 64 columns of D2 ----
             mbar_wait(d2_full, d2f_phase); d2f_phase ^= 1;
             tc_fence_after();
