@@ -617,7 +617,8 @@ def test_full_size_cfg3_cityscapes_T10_against_oracle():
     cfg = O.OracleConfig(task="seg", num_classes=19, timesteps=10)
     W = O.make_weights(cfg, seed=43)
     x, noise = O.make_inputs(cfg, 1, 128, 256, seed=92)
-    P.check_seg_parity(make_engine(cfg, W, "tc_3xf16"), W, cfg, x, noise, "BASELINE cfg3 128x256 C19 T10 [tc_3xf16]")
+    ref = O.sample(W, cfg, x, noise)           # open loop as well: the record then says how the FINAL map compares
+    P.check_seg_parity(make_engine(cfg, W, "tc_3xf16"), W, cfg, x, noise, "BASELINE cfg3 128x256 C19 T10 [tc_3xf16]", ref=ref)
 
 
 def test_full_size_cfg2_ade_T3_accumulation_against_oracle():
@@ -625,7 +626,8 @@ def test_full_size_cfg2_ade_T3_accumulation_against_oracle():
     cfg = O.OracleConfig(task="seg", num_classes=150, timesteps=3, accumulation=True)
     W = O.make_weights(cfg, seed=44)
     x, noise = O.make_inputs(cfg, 1, 128, 128, seed=93)
-    P.check_seg_parity(make_engine(cfg, W, "tc_3xf16"), W, cfg, x, noise, "BASELINE cfg2 128x128 C150 T3 acc [tc_3xf16]")
+    ref = O.sample(W, cfg, x, noise)
+    P.check_seg_parity(make_engine(cfg, W, "tc_3xf16"), W, cfg, x, noise, "BASELINE cfg2 128x128 C150 T3 acc [tc_3xf16]", ref=ref)
 
 
 def test_full_size_cfg4_depth_T20_against_oracle():
