@@ -77,6 +77,7 @@ struct ddp_handle {
     bool ffn_pull = true;           // DDP_B200_FFN_PULL: chunk 0 of the next tile ahead of the current tile's LayerNorm (ffn_fused.cuh)
     bool gemm_tma_stores = true;    // DDP_B200_GEMM_TMA_STORES: out_proj / head_in write their q planes through TMA box stores
     bool ffn_tma_stores = true;     // DDP_B200_FFN_TMA_STORES: the fused FFN's new q planes leave through TMA box stores
+    bool qproj_pew_early = true;    // DDP_B200_QPROJ_PEW_EARLY
     bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
     int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
@@ -702,6 +703,8 @@ int ddp_create(const ddp_config* cfg, ddp_handle** out) {
         h->gemm_tma_stores = gs == nullptr || atoi(gs) != 0;            // default on; 0 = per-thread staged stores
         const char* fs = getenv("DDP_B200_FFN_TMA_STORES");
         h->ffn_tma_stores = fs == nullptr || atoi(fs) != 0;             // default on; 0 = per-thread staged stores
+        const char* pe2 = getenv("DDP_B200_QPROJ_PEW_EARLY");
+        h->qproj_pew_early = pe2 == nullptr || atoi(pe2) != 0;
         const char* ts = getenv("DDP_B200_QPROJ_TMA_STORES");
         h->qproj_tma_stores = ts == nullptr || atoi(ts) != 0;           // default on; 0 = per-thread staged stores
         const char* ct = getenv("DDP_B200_COND_TC");
@@ -1026,6 +1029,7 @@ static int run_denoiser(ddp_handle* h, const Workspace& ws, int k, const float* 
                 qp.samp.scale = T.s.inv_scale; qp.samp.out = want_s ? ws.samp : nullptr; qp.samp.ldc = kSampW; qp.samp.ncols = kSampW;
                 qp.samp.pew = h->pew[j]; qp.samp.N_tok = N; qp.samp.rec = ws.rec; qp.samp.H = h->H; qp.samp.W = h->W;
                 qp.tma_stores = h->qproj_tma_stores ? 1 : 0;
+                qp.pew_early = h->qproj_pew_early ? 1 : 0;
                 prof_begin(h, DDP_K_QPROJ_FUSED, st);
                 cudaError_t e_ = s3 ? tc::launch_qproj_fused<3>(h->mA_q[0], h->mA_q[1], T.v.map_half_hi, T.v.map_half_lo,
                                                                 T.s.map_pair_hi, T.s.map_pair_lo, h->mS_V, h->mS_rec, M, kE, qp, h->num_sms, st)

@@ -473,10 +473,26 @@ struct EpiParams {
 // (head, point), 64..95 attention logits, 96..127 padding.  Four warps per TMEM lane quarter: warp `half` (0..3) owns
 // heads 2*half and 2*half + 1, i.e. offset columns [16 half, +16) and logits [64 + 8 half, +8); it writes the matching
 // 32-byte pieces of the four record sections (index words, fx, fy, attention weights).  `stg` = this warp's >= 1 KB tile.
+// This row's share of pew = PE * W_s^T + b_s (16 offsets + 8 logits of the warp's two heads): six 16-byte loads at a
+// 384-byte row stride, i.e. L2-latency loads.  A caller whose epilogue is on the critical path issues them EARLY (before
+// waiting for the accumulator) and hands them to sampling_epilogue.
+struct PewRow { float4 o[4]; float4 a[2]; };
+__device__ __forceinline__ PewRow sampling_prefetch(const EpiParams& ep, int half, size_t srow) {
+    const int n = (int)(srow % ep.N_tok);
+    const float* pp = ep.pew + (size_t)n * kSampW;
+    PewRow r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.o[i] = __ldg(reinterpret_cast<const float4*>(pp + 16 * half + i * 4));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r.a[i] = __ldg(reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4));
+    return r;
+}
+
 // rec_map != nullptr: the record pieces leave through TMA box stores (map over rec as [M][128] 32-bit words, box {8, 32},
 // SWIZZLE_32B) instead of per-thread stores; the caller owns the bulk-group discipline of `stg` (stage_tma_sync).
 __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t t_row, int half, int wrow0, size_t srow,
-                                                  int rows_valid, int lane, float* stg, const CUtensorMap* rec_map = nullptr) {
+                                                  int rows_valid, int lane, float* stg, const CUtensorMap* rec_map = nullptr,
+                                                  const PewRow* pre = nullptr) {
     const int n = (int)(srow % ep.N_tok);
     __half* rech = reinterpret_cast<__half*>(ep.rec + (size_t)wrow0 * kRecW);       // 2 halves per record word
     const float* pp = ep.pew + (size_t)n * kSampW;
@@ -485,13 +501,13 @@ __device__ __forceinline__ void sampling_epilogue(const EpiParams& ep, uint32_t 
     tmem_ld8(t_row + 64 + 8 * half, a);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float4 p4 = *reinterpret_cast<const float4*>(pp + 16 * half + i * 4);
+        const float4 p4 = pre ? pre->o[i] : *reinterpret_cast<const float4*>(pp + 16 * half + i * 4);
         o[i * 4 + 0] = fmaf(o[i * 4 + 0], ep.scale, p4.x); o[i * 4 + 1] = fmaf(o[i * 4 + 1], ep.scale, p4.y);
         o[i * 4 + 2] = fmaf(o[i * 4 + 2], ep.scale, p4.z); o[i * 4 + 3] = fmaf(o[i * 4 + 3], ep.scale, p4.w);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const float4 p4 = *reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4);
+        const float4 p4 = pre ? pre->a[i] : *reinterpret_cast<const float4*>(pp + 64 + 8 * half + i * 4);
         a[i * 4 + 0] = fmaf(a[i * 4 + 0], ep.scale, p4.x); a[i * 4 + 1] = fmaf(a[i * 4 + 1], ep.scale, p4.y);
         a[i * 4 + 2] = fmaf(a[i * 4 + 2], ep.scale, p4.z); a[i * 4 + 3] = fmaf(a[i * 4 + 3], ep.scale, p4.w);
     }

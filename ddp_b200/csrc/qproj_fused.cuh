@@ -31,6 +31,7 @@ struct QprojParams {
     float* V;                // [M][256] fp32
     EpiParams samp;          // scale, pew, N_tok, H, W, rec, out (optional raw tap), ldc: as for EPI_SAMPLING
     int tma_stores;          // 1: the value tile and the records leave through TMA box stores (mapVout / mapRec)
+    int pew_early;           // 1: this row's pew values are loaded before the value tile (their L2 latency hides under it)
 };
 
 constexpr int kQpThreads = 32 * 19;                   // A producer, MMA issuer, 16 epilogue warps, weight producer
@@ -206,6 +207,8 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             const int row = wrow0 + lane;
             const int rows_valid = M - wrow0 < 0 ? 0 : (M - wrow0 > 32 ? 32 : M - wrow0);
             const size_t srow = row < M ? (size_t)row : (size_t)(M - 1);
+            PewRow pw;
+            if (p.pew_early) pw = sampling_prefetch(p.samp, part, srow);
             // ---- value tile: V = acc * scale + bias ----
             // Both 32-column blocks are pulled into registers FIRST and V's TMEM columns are released at once: V is single
             // buffered, so the next round's V MMAs wait for this release — with the release after the stores (round 1) the
@@ -243,7 +246,7 @@ qproj_fused_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             mbar_wait(&s_full[sbuf], sfph[sbuf]); sfph[sbuf] ^= 1;
             tc_fence_after();
             sampling_epilogue(p.samp, tS + (uint32_t)sbuf * 128u + lane_sel, part, wrow0, srow, rows_valid, lane, stg,
-                              p.tma_stores ? &mapRec : nullptr);
+                              p.tma_stores ? &mapRec : nullptr, p.pew_early ? &pw : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&s_empty[sbuf]);
