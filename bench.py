@@ -266,10 +266,12 @@ def measure(name, wl, args, ctx, steps, warmup, with_clocks=False):
     x_bytes = B * E * wl["h"] * wl["w"] * 4
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if x_bytes < (192 << 20) else None
 
+    out_fixed = torch.empty((B, eng.num_classes, wl["h"], wl["w"]), dtype=torch.float32, device=dev)
+
     def step_device():
         if flush_buf is not None:
             flush_buf.zero_()
-        out = eng.sample(xd, nd)
+        out = eng.sample(xd, nd, out=out_fixed)          # fixed result buffer (what DDP_B200_GRAPH=1 keys its CUDA graph on)
         if world > 1:
             dist.all_gather_into_tensor(gathered, out)     # the single gather of final logits
         return out
@@ -475,6 +477,10 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
     ctx = dict(dev=dev, world=world, rank=rank, local=local, dist=dist)
+    # everything below runs on a dedicated (non-default) stream: the library is asynchronous on the caller's stream, and the
+    # opt-in CUDA-graph mode (DDP_B200_GRAPH=1) cannot capture the legacy default stream
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 
     warmup = max(args.warmup, 3)
     res = measure(args.workload, wl, args, ctx, args.steps, warmup, with_clocks=True)
