@@ -182,7 +182,9 @@ __global__ void k_embed_lut(const float* __restrict__ emb, float* __restrict__ l
 // The sampling positions were resolved by the sampling projection's epilogue (msda_resolve, common.cuh): this kernel
 // is loads + FMAs only, no branches.  One warp per token; lane = (head-in-group = lane / 8, 4 channels); the warp walks
 // two groups of 4 heads so that every warp-wide float4 load covers four whole 128-byte lines (one per head).
-__global__ void __launch_bounds__(256, 4)
+// launch_bounds(256, 6): 40 registers, 48 resident warps — 3 % faster than (256, 4) / 64 registers in tools/ubench_gather.cu
+// (v7: 3 / 4 / 5 / 6 / 8 CTAs per SM = 0.310 / 0.262 / 0.261 / 0.254 / 0.292 ms)
+__global__ void __launch_bounds__(256, 6)
 k_msda_gather(const float* __restrict__ V, const uint32_t* __restrict__ rec, float* __restrict__ out,
               __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int W, int total_tokens) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

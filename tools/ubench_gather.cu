@@ -243,6 +243,73 @@ k_msda_gather_old(const float* __restrict__ V, const uint32_t* __restrict__ rec,
 }
 
 
+// v7: the product kernel with other occupancy targets (register caps 51 / 42 / 32 -> 40 / 48 / 64 warps per SM)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_msda_gather_lb(const float* __restrict__ V, const uint32_t* __restrict__ rec, float* __restrict__ out,
+              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int N, int W, int total_tokens) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= total_tokens) return;
+    int lane = threadIdx.x & 31;
+    int row = warp / N;
+    const uint32_t* rp = rec + (size_t)warp * kRecW;
+#pragma unroll
+    for (int hg = 0; hg < 2; ++hg) {
+        const int m = hg * 4 + (lane >> 3);
+        const int ch = m * kHeadDim + (lane & 7) * 4;
+        const float* Vr = V + (size_t)row * N * kE + ch;
+        const uint4 wd = *reinterpret_cast<const uint4*>(rp + m * 4);
+        const float4 fx = *reinterpret_cast<const float4*>(rp + 32 + m * 4);
+        const float4 fy = *reinterpret_cast<const float4*>(rp + 64 + m * 4);
+        const float4 aw = *reinterpret_cast<const float4*>(rp + 96 + m * 4);
+        const uint32_t w4[4] = {wd.x, wd.y, wd.z, wd.w};
+        const float fx4[4] = {fx.x, fx.y, fx.z, fx.w}, fy4[4] = {fy.x, fy.y, fy.z, fy.w}, a4[4] = {aw.x, aw.y, aw.z, aw.w};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        // all 16 corner loads of this head group are issued before any is used (memory-level parallelism)
+        float4 vv[kPoints][4];
+#pragma unroll
+        for (int p = 0; p < kPoints; ++p) {
+            const uint32_t wv = w4[p];
+            const int base = (int)(wv & 0x03FFFFFFu);
+            const int dx = (int)((wv >> 26) & 1u);
+            const int dy = ((wv >> 27) & 1u) ? W : 0;
+            vv[p][0] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)base * kE));
+            vv[p][1] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dx) * kE));
+            vv[p][2] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy) * kE));
+            vv[p][3] = __ldg(reinterpret_cast<const float4*>(Vr + (size_t)(base + dy + dx) * kE));
+        }
+#pragma unroll
+        for (int p = 0; p < kPoints; ++p) {
+            const uint32_t wv = w4[p];
+            const float wx1 = fx4[p], wy1 = fy4[p], wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+            const float c00 = (wv & (1u << 28)) ? wy0 * wx0 : 0.f;
+            const float c01 = (wv & (1u << 29)) ? wy0 * wx1 : 0.f;
+            const float c10 = (wv & (1u << 30)) ? wy1 * wx0 : 0.f;
+            const float c11 = (wv & (1u << 31)) ? wy1 * wx1 : 0.f;
+            const float4 v00 = vv[p][0], v01 = vv[p][1], v10 = vv[p][2], v11 = vv[p][3];
+            float s0 = c00 * v00.x, s1 = c00 * v00.y, s2 = c00 * v00.z, s3 = c00 * v00.w;
+            s0 = fmaf(c01, v01.x, s0); s1 = fmaf(c01, v01.y, s1); s2 = fmaf(c01, v01.z, s2); s3 = fmaf(c01, v01.w, s3);
+            s0 = fmaf(c10, v10.x, s0); s1 = fmaf(c10, v10.y, s1); s2 = fmaf(c10, v10.z, s2); s3 = fmaf(c10, v10.w, s3);
+            s0 = fmaf(c11, v11.x, s0); s1 = fmaf(c11, v11.y, s1); s2 = fmaf(c11, v11.z, s2); s3 = fmaf(c11, v11.w, s3);
+            acc[0] = fmaf(a4[p], s0, acc[0]); acc[1] = fmaf(a4[p], s1, acc[1]);
+            acc[2] = fmaf(a4[p], s2, acc[2]); acc[3] = fmaf(a4[p], s3, acc[3]);
+        }
+        const size_t o = (size_t)warp * kE + ch;
+        if (out) *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (out_hi) {
+            const float a0 = acc[0] * kSplitScale, a1 = acc[1] * kSplitScale, a2 = acc[2] * kSplitScale, a3 = acc[3] * kSplitScale;
+            __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+            *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h23));
+            if (out_lo) {
+                const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+                __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y), l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+                *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(*reinterpret_cast<uint32_t*>(&l01), *reinterpret_cast<uint32_t*>(&l23));
+            }
+        }
+    }
+}
+
+
 // one head group (4 heads) of one token: the body of k_msda_gather, verbatim arithmetic
 __device__ __forceinline__ void gather_group(const float* __restrict__ V, const uint32_t* __restrict__ rec, __half* out_hi,
                                              __half* out_lo, int N, int W, int token, int hg, int lane) {
@@ -576,6 +643,21 @@ int main(int argc, char** argv) {
                    bad ? "OUTPUT DIFFERS " : "bit-identical ", e == cudaSuccess ? "" : cudaGetErrorString(e));
             if (bad || e != cudaSuccess) rc = 2;
         };
+        auto run7 = [&](const char* name, auto kern) {
+            cudaMemset(hi1, 0, (size_t)total * kE * 2);
+            auto l = [&]() { kern<<<(unsigned)(((size_t)total * 32 + 255) / 256), 256>>>(V, rec, nullptr, hi1, lo1, N, W, total); };
+            const float ms = time_ms(l, 20);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaMemcpy(got.data(), hi1, got.size() * 2, cudaMemcpyDeviceToHost);
+            size_t bad = 0;
+            for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+            printf("               %-32s            %.3f ms  (%.2fx of v0)  %s%s\n", name, ms, ms0 / ms,
+                   bad ? "OUTPUT DIFFERS " : "bit-identical ", e == cudaSuccess ? "" : cudaGetErrorString(e));
+        };
+        run7("v7 launch_bounds(256, 3)", k_msda_gather_lb<3>);
+        run7("v7 launch_bounds(256, 5)", k_msda_gather_lb<5>);
+        run7("v7 launch_bounds(256, 6)", k_msda_gather_lb<6>);
+        run7("v7 launch_bounds(256, 8)", k_msda_gather_lb<8>);
         run6("v6 no prefetch (gather_group x2)", k_gather_pf<0>);
         run6("v6 L1 prefetch of head group 1", k_gather_pf<1>);
         run6("v6 L1 prefetch hg0 batch 2", k_gather_pf<2>);
