@@ -96,6 +96,62 @@ __global__ void __launch_bounds__(256) k_gn_finalize_warp(GnFinalize f, size_t n
     }
 }
 
+// GnApply / MsmMerge, four channels per thread (float4 loads and stores; per-element arithmetic identical to the functors
+// of neck_plan.h, which the host emulation keeps using).  The scalar forms were 25 % + 16 % of the neck after the
+// convolutions moved to the tensor cores.
+__global__ void __launch_bounds__(256) k_gn_apply4(GnApply f, size_t n4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int C4 = f.C / 4;
+    const int c = (int)(i4 % C4) * 4;
+    const size_t t = i4 / C4;
+    const int n = (int)(t % f.N);
+    const size_t b = t / f.N;
+    const int g = c / (f.C / f.G);                       // the four channels share a group (C / G is a multiple of 4)
+    const float mean = f.stats[(b * f.G + g) * 2], rstd = f.stats[(b * f.G + g) * 2 + 1];
+    const float4 x = *reinterpret_cast<const float4*>(f.src + i4 * 4);
+    const float4 ga = *reinterpret_cast<const float4*>(f.gamma + c), be = *reinterpret_cast<const float4*>(f.beta + c);
+    float4 y;
+    y.x = (x.x - mean) * rstd * ga.x + be.x; y.y = (x.y - mean) * rstd * ga.y + be.y;
+    y.z = (x.z - mean) * rstd * ga.z + be.z; y.w = (x.w - mean) * rstd * ga.w + be.w;
+    if (f.up) {
+        const int i = n / f.W, j = n - i * f.W;
+        const int iu = nearest_src(i, f.sh, f.Hu), ju = nearest_src(j, f.sw, f.Wu);
+        const float4 u = *reinterpret_cast<const float4*>(f.up + ((b * f.Hu + iu) * (size_t)f.Wu + ju) * f.C + c);
+        y.x += u.x; y.y += u.y; y.z += u.z; y.w += u.w;
+    }
+    *reinterpret_cast<float4*>(f.dst + i4 * 4) = y;
+}
+__global__ void __launch_bounds__(256) k_msm_merge4(MsmMerge m, size_t n4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int C4 = m.C / 4;
+    const int c = (int)(i4 % C4) * 4;
+    const size_t t = i4 / C4;
+    const int N0 = m.H[0] * m.W[0];
+    const int n = (int)(t % N0);
+    const size_t b = t / N0;
+    const int i = n / m.W[0], j = n - i * m.W[0];
+    float4 acc = *reinterpret_cast<const float4*>(m.z[0] + i4 * 4);
+#pragma unroll
+    for (int l = 1; l < kMaxLevels; ++l) {
+        if (l >= m.L) break;
+        const int h = m.H[l], w = m.W[l];
+        int y0, y1, x0, x1; float ly, lx;
+        bilinear_src(i, (float)h / (float)m.H[0], h, y0, y1, ly);
+        bilinear_src(j, (float)w / (float)m.W[0], w, x0, x1, lx);
+        const float hy = 1.0f - ly, hx = 1.0f - lx;
+        const float* p = m.z[l] + b * (size_t)h * w * m.C + c;
+        const float4 p00 = *reinterpret_cast<const float4*>(p + ((size_t)y0 * w + x0) * m.C), p01 = *reinterpret_cast<const float4*>(p + ((size_t)y0 * w + x1) * m.C);
+        const float4 p10 = *reinterpret_cast<const float4*>(p + ((size_t)y1 * w + x0) * m.C), p11 = *reinterpret_cast<const float4*>(p + ((size_t)y1 * w + x1) * m.C);
+        acc.x += hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+        acc.y += hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+        acc.z += hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+        acc.w += hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+    }
+    *reinterpret_cast<float4*>(m.dst + i4 * 4) = acc;
+}
+
 struct NeckTc {
     bool on = false;
     int num_sms = 148;
@@ -117,6 +173,18 @@ struct CudaBackend {
     void for_each(size_t n, const F& f) {
         if (n == 0) return;
         k_for_each<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n);
+        ++launches;
+    }
+    void for_each(size_t n, const GnApply& f) {             // overloads: four channels per thread
+        if (n == 0) return;
+        if (f.C % 4 || (f.C / f.G) % 4) { k_for_each<GnApply><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n); ++launches; return; }
+        k_gn_apply4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+        ++launches;
+    }
+    void for_each(size_t n, const MsmMerge& m) {
+        if (n == 0) return;
+        if (m.C % 4) { k_for_each<MsmMerge><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, n); ++launches; return; }
+        k_msm_merge4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(m, n / 4);
         ++launches;
     }
     void for_each(size_t n, const GnFinalize& f) {          // overload: one warp per (image, group)
