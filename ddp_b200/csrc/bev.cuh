@@ -66,6 +66,72 @@ std::string bev_inner_key(const std::string& k) {
     return k;                                   // embedding_table.weight, time_mlp.*
 }
 
+// GridSample / StepUpdate with four channels per thread (float4 loads / stores; the geometry, the six sigmoids of the source
+// pixel and the schedule arithmetic are computed once per thread instead of once per channel; per-element arithmetic
+// identical to the functors of bev_plan.h, which the host emulation keeps using)
+__global__ void __launch_bounds__(256) k_bev_grid_sample4(ddp::bev::GridSample f, size_t n4) {
+    using namespace ddp::bev;
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int c = (int)(i4 % (kEmbed / 4)) * 4;
+    const size_t t = i4 / (kEmbed / 4);
+    const size_t n_out = (size_t)f.Ho * f.Wo;
+    const int n = (int)(t % n_out);
+    const size_t row = t / n_out;
+    const int Y = n / f.Wo, X = n - Y * f.Wo;
+    const float x = (f.grid_x[X] + 1.0f) * ((float)f.w * 0.5f) - 0.5f;
+    const float y = (f.grid_y[Y] + 1.0f) * ((float)f.h * 0.5f) - 0.5f;
+    const float xf = floorf(x), yf = floorf(y);
+    const float wx1 = x - xf, wy1 = y - yf, wx0 = 1.0f - wx1, wy0 = 1.0f - wy1;
+    const int x0 = (xf >= -2.0f && xf <= (float)f.w) ? (int)xf : -2;
+    const int y0 = (yf >= -2.0f && yf <= (float)f.h) ? (int)yf : -2;
+    const float* p = f.src + row * (size_t)f.h * f.w * kEmbed + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto add = [&](int yy, int xx, float wgt) {
+        const float4 v = *reinterpret_cast<const float4*>(p + ((size_t)yy * f.w + xx) * kEmbed);
+        acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+    };
+    if (y0 >= 0 && y0 < f.h) {
+        if (x0 >= 0 && x0 < f.w) add(y0, x0, wy0 * wx0);
+        if (x0 + 1 >= 0 && x0 + 1 < f.w) add(y0, x0 + 1, wy0 * wx1);
+    }
+    if (y0 + 1 >= 0 && y0 + 1 < f.h) {
+        if (x0 >= 0 && x0 < f.w) add(y0 + 1, x0, wy1 * wx0);
+        if (x0 + 1 >= 0 && x0 + 1 < f.w) add(y0 + 1, x0 + 1, wy1 * wx1);
+    }
+    *reinterpret_cast<float4*>(f.dst + i4 * 4) = acc;
+}
+__global__ void __launch_bounds__(256) k_bev_step_update4(ddp::bev::StepUpdate u, size_t n4) {
+    using namespace ddp::bev;
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= n4) return;
+    const int c = (int)(i4 % (kEmbed / 4)) * 4;
+    const size_t t = i4 / (kEmbed / 4);
+    const size_t n_state = (size_t)u.h * u.w, n_out = (size_t)u.Ho * u.Wo;
+    const int n = (int)(t % n_state);
+    const size_t row = t / n_state;
+    const int i = n / u.w, j = n - i * u.w;
+    const int Y = ddp::neck::nearest_src(i, u.sh, u.Ho), X = ddp::neck::nearest_src(j, u.sw, u.Wo);
+    const float* lp = u.logits + row * kClasses * n_out + (size_t)Y * u.Wo + X;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < kClasses; ++s) {
+        const bool on = sigmoid_f(lp[(size_t)s * n_out]) > u.threshold;
+        const float4 e = *reinterpret_cast<const float4*>(u.emb + (size_t)(on ? s + 1 : 0) * kEmbed + c);
+        sum.x += e.x; sum.y += e.y; sum.z += e.z; sum.w += e.w;
+    }
+    const float sg = u.sigma > 1e-8f ? u.sigma : 1e-8f;
+    float4 m = *reinterpret_cast<const float4*>(u.state + i4 * 4);
+    auto upd = [&](float sm, float mv) {
+        const float mean = sm / (float)kClasses;
+        const float pred = (sigmoid_f(mean) * 2.0f - 1.0f) * u.bit_scale;
+        const float eps = (mv - u.alpha * pred) / sg;
+        return pred * u.alpha_next + eps * u.sigma_next;
+    };
+    m.x = upd(sum.x, m.x); m.y = upd(sum.y, m.y); m.z = upd(sum.z, m.z); m.w = upd(sum.w, m.w);
+    *reinterpret_cast<float4*>(u.state + i4 * 4) = m;
+}
+
 struct BevCudaBackend {
     ddp_bev* h;
     void* inner_ws;
@@ -76,6 +142,16 @@ struct BevCudaBackend {
     void for_each(size_t n, const F& f) {
         if (n == 0) return;
         ddp::neck::k_for_each<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f, n);
+        ++launches;
+    }
+    void for_each(size_t n, const ddp::bev::GridSample& f) {        // overloads: four channels per thread
+        if (n == 0) return;
+        k_bev_grid_sample4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(f, n / 4);
+        ++launches;
+    }
+    void for_each(size_t n, const ddp::bev::StepUpdate& u) {
+        if (n == 0) return;
+        k_bev_step_update4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(u, n / 4);
         ++launches;
     }
     void gemm_cond(const float* x, int feat, int N, int B, const float* wx_t, const float* bias, float* cond) {
