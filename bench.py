@@ -394,7 +394,9 @@ def measure(name, wl, args, ctx, steps, warmup, with_clocks=False):
 
     res = {
         "value": value, "unit": "images/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
-        "config": workload_config(wl, name, world * B, args), "clocks": clocks,
+        "config": dict(workload_config(wl, name, world * B, args),
+                       host_numa=("rank bound to its GPU's NUMA node (%d cpus)" % len(ctx["numa_cpus"])) if ctx.get("numa_cpus") else "unbound"),
+        "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / steps, "steps": steps,
                 "api": "ddp_sample_host_submit/_wait (streaming, two calls in flight, pinned host buffers)",
@@ -472,11 +474,17 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    numa_cpus = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # one process per GPU: keep each rank (and the pinned buffers it allocates) on its GPU's NUMA node.  N = 1 is left
+        # alone: the cpu_baseline leg of that run uses every host core.  DDP_BENCH_NUMA=0 switches it off.
+        if os.environ.get("DDP_BENCH_NUMA", "1") != "0":
+            from ddp_b200.dist import bind_near_gpu
+            numa_cpus = bind_near_gpu(local)
         dist.init_process_group("nccl", device_id=dev)
-    ctx = dict(dev=dev, world=world, rank=rank, local=local, dist=dist)
+    ctx = dict(dev=dev, world=world, rank=rank, local=local, dist=dist, numa_cpus=numa_cpus)
     # everything below runs on a dedicated (non-default) stream: the library is asynchronous on the caller's stream, and the
     # opt-in CUDA-graph mode (DDP_B200_GRAPH=1) cannot capture the legacy default stream
     torch.cuda.synchronize()

@@ -1,8 +1,9 @@
 // CUDA backend + C ABI of the BEV map-segmentation variant of the decode loop — SURVEY 8f #4.
 // The launch sequence and the per-element kernel bodies live in bev_plan.h (shared with the host emulation the CPU
 // tests use).  The denoiser is NOT re-implemented: a ddp_bev owns an inner segmentation ddp_handle (6 classes,
-// num_layers = 5, planned on the OUTPUT grid) and calls the hardware-verified ddp_head_forward once per step, with the
-// step's time embedding taken from the inner handle's precomputed table.
+// num_layers = 5, planned on the OUTPUT grid) and calls the hardware-verified denoiser (head_forward_impl, the body of
+// ddp_head_forward) once per step on the tokens its grid sample wrote, with the step's FiLM vectors taken from the inner
+// handle's precomputed table.
 //
 // Included at the end of ddp_b200.cu (same translation unit: it reaches into ddp_handle).
 #pragma once
@@ -169,15 +170,9 @@ struct BevCudaBackend {
         ddp::k_nchw_to_tokens<<<grid, dim3(32, 8), 0, st>>>(src, dst, C, N);
         ++launches;
     }
-    void tokens_to_nchw(const float* src, float* dst, int imgs, int N, int C) {     // same kernel, roles swapped
-        dim3 grid((C + 31) / 32, (N + 31) / 32, imgs);
-        ddp::k_nchw_to_tokens<<<grid, dim3(32, 8), 0, st>>>(src, dst, N, C);
-        ++launches;
-    }
-    int denoise(int k, const float* feat_nchw, float* logits) {
+    int denoise(int k, const float* feat_tokens, float* /*scratch_nchw*/, float* logits) {
         ddp_handle* in = h->inner;
-        const int rc = ddp_head_forward(in, feat_nchw, in->temb + (size_t)k * ddp::kTimeDim, logits, inner_ws,
-                                        in->ws_compute_bytes, st);
+        const int rc = head_forward_impl(in, feat_tokens, true, nullptr, k, logits, inner_ws, in->ws_compute_bytes, st);
         if (rc) return bfail(h, rc, "denoiser (ddp_head_forward) failed at step %d: %s", k, ddp_last_error(in));
         launches += in->launches;
         return 0;

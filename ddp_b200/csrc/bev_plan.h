@@ -172,8 +172,10 @@ struct Zero {
 
 // The launch sequence.  x: NCHW (B, feat, h, w); noise: NCHW (B, R, 256, h, w); out: NCHW (B, 6, Ho, Wo).
 // Backend: for_each(n, functor); gemm_cond(x, feat, n_state, B, wx_t, bias, cond); gemm_head_in(state, wm_t, cond,
-// n_state, R, rows, q); nchw_to_tokens(src, dst, imgs, C, N); tokens_to_nchw(src, dst, imgs, N, C);
-// denoise(step, feat_nchw, logits_nchw) -> 0 or an error code.
+// n_state, R, rows, q); nchw_to_tokens(src, dst, imgs, C, N);
+// denoise(step, feat_tokens, scratch_nchw, logits_nchw) -> 0 or an error code: the denoiser's input arrives as tokens
+// ((rows, n_out, 256), what GridSample writes); a backend whose denoiser wants decode_head.forward's NCHW layout transposes
+// into scratch_nchw itself (the host emulation does, the CUDA denoiser consumes tokens directly).
 template <class Backend>
 int bev_run(Backend& be, const Dims& d, const Weights& w, const Schedule& sch, const Buffers& buf, const float* x,
             const float* noise, float* out) {
@@ -185,8 +187,7 @@ int bev_run(Backend& be, const Dims& d, const Weights& w, const Schedule& sch, c
     for (int k = 0; k < d.T; ++k) {
         be.gemm_head_in(buf.state, w.wm_t, buf.cond, (int)ns, d.R, rows, buf.q_state);      // transform(cat[x, mask_t])
         be.for_each((size_t)rows * no * kEmbed, GridSample{buf.q_state, buf.q_out, w.grid_y, w.grid_x, d.h, d.w, d.Ho, d.Wo});
-        be.tokens_to_nchw(buf.q_out, buf.feat_nchw, rows, (int)no, kEmbed);
-        const int rc = be.denoise(k, buf.feat_nchw, buf.logits);                            // 5 x (MSDA, LN, FFN, LN, FiLM) + conv_seg
+        const int rc = be.denoise(k, buf.q_out, buf.feat_nchw, buf.logits);                 // 5 x (MSDA, LN, FFN, LN, FiLM) + conv_seg
         if (rc) return rc;
         be.for_each((size_t)d.B * kClasses * no, Accumulate{buf.logits, buf.accum, d.R, no});
         StepUpdate u{buf.logits, w.emb, buf.state, d.h, d.w, d.Ho, d.Wo, (float)d.Ho / (float)d.h, (float)d.Wo / (float)d.w,

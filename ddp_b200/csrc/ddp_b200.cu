@@ -1421,11 +1421,16 @@ const char* ddp_kernel_class_name(int cls) {
     return (cls >= 0 && cls < DDP_K_COUNT) ? names[cls] : nullptr;
 }
 
-int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embedding, float* out, void* workspace,
-                     size_t workspace_bytes, void* stream) {
+// One denoiser evaluation.  The exported ddp_head_forward passes an NCHW input and the caller's time embedding; the BEV loop
+// (bev.cuh, same translation unit) passes tokens ((rows, N, 256), what its grid sample writes) and a step of the handle's
+// own schedule, whose FiLM vectors compute_time_constants already holds: no layout round trip and no per-call gemv.
+static int head_forward_impl(ddp_handle* h, const float* feat, bool feat_tokens, const float* time_embedding, int sched_step,
+                             float* out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h) return DDP_ERR_INVALID;
     if (!h->planned) return fail(h, DDP_ERR_STATE, "ddp_head_forward: call ddp_plan first");
-    if (!feat || !time_embedding || !out || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_head_forward: null pointer");
+    if (!feat || (!time_embedding && sched_step < 0) || !out || !workspace) return fail(h, DDP_ERR_INVALID, "ddp_head_forward: null pointer");
+    if (sched_step >= h->cfg.timesteps || (sched_step >= 0 && h->time_dirty))
+        return fail(h, DDP_ERR_STATE, "ddp_head_forward: schedule step %d is not available", sched_step);
     if (workspace_bytes < h->ws_compute_bytes)
         return fail(h, DDP_ERR_WORKSPACE, "ddp_head_forward: workspace %zu < required %zu", workspace_bytes, h->ws_compute_bytes);
     if (reinterpret_cast<uintptr_t>(workspace) % 256)
@@ -1442,7 +1447,7 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
     if (h->tc && (rc = ensure_activation_maps(h, workspace, ws, 0, h->B))) return rc;
     // FiLM vectors of the caller's embedding: time_mlp = SiLU -> Linear(1024 -> 512) per layer (transformer.py:275-278, 413-417)
     dim3 g2((2 * kE * 32 + 255) / 256, 1);
-    for (int j = 0; j < Lc; ++j) {
+    for (int j = 0; j < Lc && sched_step < 0; ++j) {
         k_gemv<1, 0><<<g2, 256, 0, st>>>(h->L[j].Wt, h->L[j].bt, time_embedding, h->film_one + (size_t)j * 2 * kE, 2 * kE, kTimeDim,
                                          kTimeDim, Lc * 2 * kE);
         LAUNCH_CHECK(h);
@@ -1452,15 +1457,26 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
     }
     // (rows, 256, h, w) -> tokens (+ fp16 planes)
     {
-        dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
-        KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(feat, ws.q, kE, N)));
+        const float* tokens = feat;
+        if (!feat_tokens) {
+            dim3 grid((N + 31) / 32, kE / 32, rows), block(32, 8);
+            KLAUNCH(h, DDP_K_LAYOUT, st, (k_nchw_to_tokens<<<grid, block, 0, st>>>(feat, ws.q, kE, N)));
+            tokens = ws.q;
+        } else if (!h->tc) {        // the fp32 path reads ws.q itself (the tensor-core path only its fp16 planes)
+            CUDA_TRY(h, cudaMemcpyAsync(ws.q, feat, (size_t)M * kE * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        }
         if (h->tc) {
             size_t n8 = (size_t)M * kE / 8;
             KLAUNCH(h, DDP_K_LAYOUT, st, (k_split_planes<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(
-                                              ws.q, ws.q_hi, h->nsplit == 3 ? ws.q_lo : nullptr, n8)));
+                                              tokens, ws.q_hi, h->nsplit == 3 ? ws.q_lo : nullptr, n8)));
         }
     }
-    if ((rc = run_denoiser(h, ws, -1, h->film_one, h->fg_one, h->fb_one, st))) return rc;
+    if (sched_step >= 0)
+        rc = run_denoiser(h, ws, -1, h->film + (size_t)sched_step * Lc * 2 * kE, h->film_g + (size_t)sched_step * Lc * kE,
+                          h->film_b + (size_t)sched_step * Lc * kE, st);
+    else
+        rc = run_denoiser(h, ws, -1, h->film_one, h->fg_one, h->fb_one, st);
+    if (rc) return rc;
     if (seg) {          // logits tokens -> (rows, C, h, w)
         const int C = c.num_classes;
         dim3 grid((N + 31) / 32, (C + 31) / 32, rows), block(32, 8);
@@ -1474,6 +1490,11 @@ int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embeddi
         KLAUNCH(h, DDP_K_STEP, st, (k_depth_step<<<(rows * N + 255) / 256, 256, 0, st>>>(p)));
     }
     return DDP_OK;
+}
+
+int ddp_head_forward(ddp_handle* h, const float* feat, const float* time_embedding, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    return head_forward_impl(h, feat, false, time_embedding, -1, out, workspace, workspace_bytes, stream);
 }
 
 int ddp_resize_argmax(ddp_handle* h, const float* logits, int B, int C, int in_h, int in_w, int out_h, int out_w,

@@ -6,6 +6,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_near_gpu(device_index):
+    """Restrict this process to the CPU cores NVML reports as local to CUDA device `device_index` (the GPU's NUMA node).
+    Pinned host buffers allocated afterwards are then first-touched on that node, so one rank's host<->device copies do
+    not cross the socket interconnect while the other ranks copy too (one process per GPU, 8 per box).  Call it before
+    allocating pinned memory.  Returns the sorted CPU list, or None when nothing was changed (no NVML, no topology
+    information, or the process is already confined to a subset): never raises."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, ((os.cpu_count() or 64) + 63) // 64)
+        near = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        have = os.sched_getaffinity(0)
+        want = near & have
+        if not want or want == have:
+            return None
+        os.sched_setaffinity(0, want)
+        return sorted(want)
+    except Exception:
+        return None
+
+
 def shard_bounds(batch, world_size, rank):
     """Contiguous shard [lo, hi) of `batch` images for `rank` (sizes differ by at most one)."""
     base, rem = divmod(batch, world_size)

@@ -64,7 +64,8 @@ struct HostBackend {
             for (int n = 0; n < N; ++n)
                 for (int c = 0; c < C; ++c) dst[((size_t)b * C + c) * N + n] = src[((size_t)b * N + n) * C + c];
     }
-    int denoise(int k, const float* feat_nchw, float* logits) {
+    int denoise(int k, const float* feat_tokens, float* feat_nchw, float* logits) {
+        tokens_to_nchw(feat_tokens, feat_nchw, d.rows(), (int)d.n_out(), kEmbed);     // decode_head.forward takes NCHW
         const size_t nf = (size_t)d.rows() * kEmbed * d.n_out(), nl = (size_t)d.rows() * kClasses * d.n_out();
         memcpy(feat_dump + (size_t)k * nf, feat_nchw, nf * sizeof(float));
         memcpy(logits, replay + (size_t)k * nl, nl * sizeof(float));
