@@ -31,6 +31,12 @@ struct ddp_bev {
     std::vector<int64_t> numels;
     float* w_arena = nullptr;                // wx_t | wm_t | b_tr | emb
     float* g_arena = nullptr;                // grid_y | grid_x
+    // tensor-core head-in (q = cond + W_m m_t on the state grid), when the inner handle runs a tc_* gemm mode
+    float* tr_w_dev = nullptr;               // transform.conv.weight as the reference stores it, (256, feat + 256)
+    __half* tc_arena = nullptr;              // W_m as scaled fp16 planes
+    TcWeight tc_in;
+    CUtensorMap mA_state[2];                 // m_t planes of the workspace the maps were last made for
+    const void* maps_ws = nullptr;
     ddp::bev::Weights w{};
     ddp::bev::Dims dims{};
     size_t own_bytes = 0, ws_bytes = 0;
@@ -102,7 +108,8 @@ __global__ void __launch_bounds__(256) k_bev_grid_sample4(ddp::bev::GridSample f
     }
     *reinterpret_cast<float4*>(f.dst + i4 * 4) = acc;
 }
-__global__ void __launch_bounds__(256) k_bev_step_update4(ddp::bev::StepUpdate u, size_t n4) {
+// hi / lo: optional fp16 planes of the new state (16 x, hi + lo as split8_store writes them) for the tensor-core head-in
+__global__ void __launch_bounds__(256) k_bev_step_update4(ddp::bev::StepUpdate u, size_t n4, __half* hi, __half* lo) {
     using namespace ddp::bev;
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= n4) return;
@@ -131,12 +138,39 @@ __global__ void __launch_bounds__(256) k_bev_step_update4(ddp::bev::StepUpdate u
     };
     m.x = upd(sum.x, m.x); m.y = upd(sum.y, m.y); m.z = upd(sum.z, m.z); m.w = upd(sum.w, m.w);
     *reinterpret_cast<float4*>(u.state + i4 * 4) = m;
+    if (hi) {
+        const float v[4] = {m.x, m.y, m.z, m.w};
+        __align__(8) __half hh[4];
+        __align__(8) __half ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float sc = fminf(fmaxf(v[e] * ddp::kSplitScale, -65504.0f), 65504.0f);
+            hh[e] = __float2half_rn(sc);
+            ll[e] = __float2half_rn(sc - __half2float(hh[e]));
+        }
+        *reinterpret_cast<uint2*>(hi + i4 * 4) = *reinterpret_cast<const uint2*>(hh);
+        if (lo) *reinterpret_cast<uint2*>(lo + i4 * 4) = *reinterpret_cast<const uint2*>(ll);
+    }
+}
+
+// q = cond + W_m m_t on tcgen05 (the segmentation loop's head-in GEMM, EPI_ADD_COND, fp32 output for the grid sample)
+static int bev_head_in_tc(ddp_bev* b, const CUtensorMap* maps, const float* cond, int N, int R, int M, float* q, cudaStream_t st) {
+    ddp_handle* h = b->inner;
+    tc::EpiParams ep{};
+    ep.scale = b->tc_in.inv_scale; ep.out = q; ep.ldc = kE; ep.ncols = kE;
+    ep.cond = cond; ep.N_tok = N; ep.R = R;
+    TC_GEMM(h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, maps, b->tc_in, M, kE, ep);
+    return DDP_OK;
 }
 
 struct BevCudaBackend {
     ddp_bev* h;
     void* inner_ws;
     cudaStream_t st;
+    __half* st_hi = nullptr;     // fp16 planes of m_t (tensor-core head-in); null = fp32 head-in
+    __half* st_lo = nullptr;
+    bool planes_valid = false;   // the planes hold the current m_t (StepUpdate writes them; the first step splits the noise)
+    int err_rc = 0;
     int64_t launches = 0;
 
     template <class F>
@@ -152,7 +186,8 @@ struct BevCudaBackend {
     }
     void for_each(size_t n, const ddp::bev::StepUpdate& u) {
         if (n == 0) return;
-        k_bev_step_update4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(u, n / 4);
+        k_bev_step_update4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(u, n / 4, st_hi, st_lo);
+        planes_valid = st_hi != nullptr;
         ++launches;
     }
     void gemm_cond(const float* x, int feat, int N, int B, const float* wx_t, const float* bias, float* cond) {
@@ -161,6 +196,18 @@ struct BevCudaBackend {
         ++launches;
     }
     void gemm_head_in(const float* state, const float* wm_t, const float* cond, int N, int R, int rows, float* q) {
+        if (st_hi) {
+            if (!planes_valid) {
+                const size_t n8 = (size_t)rows * N * ddp::kE / 8;
+                ddp::k_split_planes<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(state, st_hi, st_lo, n8);
+                planes_valid = true;
+                ++launches;
+            }
+            const int rc = bev_head_in_tc(h, h->mA_state, cond, N, R, rows * N, q, st);
+            if (rc && !err_rc) err_rc = bfail(h, rc, "tensor-core head-in failed: %s", ddp_last_error(h->inner));
+            ++launches;
+            return;
+        }
         ddp::EpiAddCond epi{q, cond, N, R, rows * N};
         ddp::launch_gemm_simt<256, 0>(state, ddp::kE, 0, wm_t, ddp::kE, rows * N, ddp::kE, ddp::kE, epi, st);
         ++launches;
@@ -172,6 +219,7 @@ struct BevCudaBackend {
     }
     int denoise(int k, const float* feat_tokens, float* /*scratch_nchw*/, float* logits) {
         ddp_handle* in = h->inner;
+        if (err_rc) return err_rc;
         const int rc = head_forward_impl(in, feat_tokens, true, nullptr, k, logits, inner_ws, in->ws_compute_bytes, st);
         if (rc) return bfail(h, rc, "denoiser (ddp_head_forward) failed at step %d: %s", k, ddp_last_error(in));
         launches += in->launches;
@@ -227,6 +275,8 @@ void ddp_bev_destroy(ddp_bev* h) {
     if (h->inner) ddp_destroy(h->inner);
     if (h->w_arena) cudaFree(h->w_arena);
     if (h->g_arena) cudaFree(h->g_arena);
+    if (h->tr_w_dev) cudaFree(h->tr_w_dev);
+    if (h->tc_arena) cudaFree(h->tc_arena);
     delete h;
 }
 
@@ -288,6 +338,25 @@ int ddp_bev_commit_weights(ddp_bev* h) {
     h->w.wm_t = h->w_arena + offs[1];
     h->w.b_tr = h->w_arena + offs[2];
     h->w.emb = h->w_arena + offs[3];
+    const char* sw = getenv("DDP_B200_BEV_HEAD_IN_TC");          // 0: keep the fp32 head-in GEMM in a tc_* gemm mode (A/B switch)
+    if (h->inner->tc && !(sw && atoi(sw) == 0)) {
+        // W_m (columns feat .. feat + 255 of the transform) as scaled fp16 planes + TMA maps, like the inner handle's tc_in
+        if (h->tr_w_dev) { cudaFree(h->tr_w_dev); h->tr_w_dev = nullptr; }
+        if (h->tc_arena) { cudaFree(h->tc_arena); h->tc_arena = nullptr; }
+        BEV_CUDA_TRY(h, cudaMalloc(&h->tr_w_dev, h->tr_w.size() * sizeof(float)));
+        BEV_CUDA_TRY(h, cudaMemcpy(h->tr_w_dev, h->tr_w.data(), h->tr_w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const size_t halves = 2 * (size_t)ddp::kE * ddp::kE;
+        BEV_CUDA_TRY(h, cudaMalloc(&h->tc_arena, halves * sizeof(__half)));
+        BEV_CUDA_TRY(h, cudaMemset(h->tc_arena, 0, halves * sizeof(__half)));
+        __half* cur = h->tc_arena;
+        const int rc = make_tc_weight(h->inner, h->tc_in, cur, ddp::kE, ddp::kE, 256,
+                                      {{h->tr_w_dev, &h->tr_w, ddp::kE, feat + ddp::kE, 1, feat, 0}}, nullptr);
+        if (rc) return bfail(h, rc, "ddp_bev_commit_weights: %s", ddp_last_error(h->inner));
+        BEV_CUDA_TRY(h, cudaDeviceSynchronize());
+    } else if (h->tc_arena) {
+        cudaFree(h->tc_arena); h->tc_arena = nullptr;
+    }
+    h->maps_ws = nullptr;
     h->committed = true;
     h->planned = false;
     return DDP_OK;
@@ -325,6 +394,7 @@ int ddp_bev_plan(ddp_bev* h, int B, int R, int in_h, int in_w, int out_h, int ou
     h->dims = d;
     h->own_bytes = carve(d, nullptr, nullptr);
     h->ws_bytes = h->own_bytes + (h->inner->ws_compute_bytes + 255) / 256 * 256;
+    h->maps_ws = nullptr;
     h->planned = true;
     if (workspace_bytes) *workspace_bytes = h->ws_bytes;
     return DDP_OK;
@@ -349,10 +419,22 @@ int ddp_bev_sample(ddp_bev* h, const float* x, const float* noise, float* out, v
     Buffers buf;
     carve(h->dims, static_cast<char*>(workspace), &buf);
     BevCudaBackend be{h, static_cast<char*>(workspace) + h->own_bytes, st};
+    if (h->tc_arena) {
+        const size_t M = (size_t)h->dims.rows() * h->dims.n_state();
+        be.st_hi = static_cast<__half*>(buf.state_planes);
+        be.st_lo = in->nsplit == 3 ? be.st_hi + M * ddp::kE : nullptr;
+        if (h->maps_ws != workspace) {
+            if (!tc::make_map_f16(&h->mA_state[0], be.st_hi, M, ddp::kE, tc::BM) ||
+                !tc::make_map_f16(&h->mA_state[1], be.st_hi + M * ddp::kE, M, ddp::kE, tc::BM))
+                return bfail(h, DDP_ERR_CUDA, "ddp_bev_sample: cuTensorMapEncodeTiled failed for the state planes");
+            h->maps_ws = workspace;
+        }
+    }
     Schedule sch{in->a_now.data(), in->s_now.data(), in->a_next.data(), in->s_next.data()};
     const int rc = bev_run(be, h->dims, h->w, sch, buf, x, noise, out);
     h->launches = be.launches;
     if (rc) return rc;
+    if (be.err_rc) return be.err_rc;
     BEV_CUDA_TRY(h, cudaGetLastError());
     return DDP_OK;
 }

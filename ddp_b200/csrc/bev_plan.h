@@ -55,9 +55,10 @@ struct Weights {                 // device (or, in the emulation, host) pointers
 struct Buffers {
     float* cond;                 // [B][n_state][256]
     float* state;                // [rows][n_state][256] m_t, token-major
+    void* state_planes;          // same bytes as `state`: room for m_t as two fp16 planes (the CUDA backend's tensor-core head-in)
     float* q_state;              // [rows][n_state][256] transform(cat[x, m_t]) on the state grid
     float* q_out;                // [rows][n_out][256]   ... resampled onto the output grid, token-major
-    float* feat_nchw;            // [rows][256][n_out]   the denoiser's input (decode_head.forward takes NCHW)
+    float* feat_nchw;            // [rows][256][n_out]   scratch for a denoiser that wants decode_head.forward's NCHW input
     float* logits;               // [rows][6][n_out]     conv_seg output before the sigmoid, NCHW
     float* accum;                // [B][6][n_out]        running sum of sigmoid maps
 };
@@ -72,6 +73,7 @@ inline size_t carve(const Dims& d, char* base, Buffers* out) {
     Buffers b{};
     b.cond = take((size_t)d.B * d.n_state() * kEmbed);
     b.state = take((size_t)d.rows() * d.n_state() * kEmbed);
+    b.state_planes = take((size_t)d.rows() * d.n_state() * kEmbed);
     b.q_state = take((size_t)d.rows() * d.n_state() * kEmbed);
     b.q_out = take((size_t)d.rows() * d.n_out() * kEmbed);
     b.feat_nchw = take((size_t)d.rows() * d.n_out() * kEmbed);
