@@ -79,7 +79,7 @@ struct ddp_handle {
     bool ffn_tma_stores = true;     // DDP_B200_FFN_TMA_STORES: the fused FFN's new q planes leave through TMA box stores
     bool qproj_pew_early = true;    // DDP_B200_QPROJ_PEW_EARLY
     bool qproj_tma_stores = true;   // DDP_B200_QPROJ_TMA_STORES: value tile + records leave the fused q-projection through TMA box stores
-    int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection run on CTA pairs
+    int gemm_pair = 0;          // DDP_B200_GEMM_PAIR bit mask: 1 value, 2 sampling, 4 output projection, 8 head-in run on CTA pairs
     bool ffn_pair = false;      // ... run by CTA pairs (cta_group::2, M = 256), each CTA streaming half of every weight tile
     unsigned long long* ffn_dbg = nullptr;   // DDP_B200_FFN_DBG=1: cycle counters of the fused kernel's MMA issuer
     int nsplit = 1;
@@ -1333,7 +1333,7 @@ static int sample_slice(ddp_handle* h, const float* x, const float* noise, float
             ep.split = tc::SplitOut{ws.q_hi, ws.q_lo, kE};
             ep.cond = ws.cond; ep.N_tok = N; ep.R = R;
             ep.tma_stores = h->gemm_tma_stores ? 1 : 0;
-            TC_GEMM(h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, h->mA_state, h->tc_in, M, kE, ep);
+            TC_GEMMP(8, h, DDP_K_HEAD_IN, st, 256, tc::EPI_ADD_COND, h->mA_state, h->tc_in, M, kE, ep);
         } else if (seg) {
             EpiAddCond epi{ws.q, ws.cond, N, R, M};
             KLAUNCH(h, DDP_K_HEAD_IN, st, (launch_gemm_simt<256, false>(ws.state, kE, 0, h->Wm_t, kE, M, kE, kE, epi, st)));
@@ -1365,7 +1365,11 @@ static int sample_slice(ddp_handle* h, const float* x, const float* noise, float
             p.row_cls = unc ? reinterpret_cast<uint8_t*>(ws.pred) : nullptr;       // ws.pred is unused by the seg loop otherwise
             p.changes = h->unc_changes ? h->unc_changes + (size_t)b0 * N : nullptr;
             p.first_step = k == 0;
-            KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<<<(unsigned)(((size_t)B * N * 32 + 255) / 256), 256, 0, st>>>(p)));
+            const unsigned step_grid = (unsigned)(((size_t)B * N * 32 + 255) / 256);
+            if (C <= 32) KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<1><<<step_grid, 256, 0, st>>>(p)));
+            else if (C <= 64) KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<2><<<step_grid, 256, 0, st>>>(p)));
+            else if (C <= 128) KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<4><<<step_grid, 256, 0, st>>>(p)));
+            else KLAUNCH(h, DDP_K_STEP, st, (k_seg_step<8><<<step_grid, 256, 0, st>>>(p)));
         } else {
             DepthStepParams p;
             p.taps = ws.logits; p.state = ws.state; p.pred = ws.pred; p.out = out;

@@ -297,6 +297,9 @@ struct SegStepParams {
 
 // One warp per image token (b, n), looping over the R stochastic samples so that the accumulation
 // order is fixed.  ddp.py:235-243: argmax -> embedding -> squash -> DDIM update; softmax accumulate.
+// KMAX = ceil(C / 32) rounded up to 1, 2, 4 or 8: the class loops are unrolled over lane + 32 k, and with 19 classes seven of
+// eight iterations (exp, IEEE division, predicated loads / stores) would be issued for nothing: the kernel is issue-bound.
+template <int KMAX>
 __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -307,11 +310,14 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
     for (int r = 0; r < p.R; ++r) {
         size_t tok = ((size_t)(b * p.R + r)) * p.N + n;
         const float* lg = p.logits + tok * C;
-        float v[8];                      // C <= 256
+        // the old state does not depend on the argmax: request it together with the logits (one DRAM latency, not two)
+        float* st = p.state + tok * kE + lane * 8;
+        const float4 mt2[2] = {*reinterpret_cast<const float4*>(st), *reinterpret_cast<const float4*>(st + 4)};
+        float v[KMAX];                   // C <= 32 KMAX
         float best = -INFINITY;
         int besti = 0x7fffffff;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
             int c = lane + k * 32;
             v[k] = (c < C) ? lg[c] : -INFINITY;
             if (c < C && (v[k] > best)) { best = v[k]; besti = c; }   // increasing c: first max wins
@@ -323,9 +329,9 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
             if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
         }
         if (p.accumulate_prob) {
-            float e[8], s = 0.f;
+            float e[KMAX], s = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 int c = lane + k * 32;
                 e[k] = (c < C) ? expf(v[k] - best) : 0.f;
                 s += e[k];
@@ -333,14 +339,14 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
             s = warp_sum(s);
             float* ac = p.accum + ((size_t)b * p.N + n) * C;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 int c = lane + k * 32;
                 if (c < C) ac[c] += e[k] / s;
             }
         } else if (p.add_logits) {
             float* ac = p.accum + ((size_t)b * p.N + n) * C;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < KMAX; ++k) {
                 int c = lane + k * 32;
                 if (c < C) ac[c] += v[k];
             }
@@ -351,12 +357,11 @@ __global__ void __launch_bounds__(256) k_seg_step(SegStepParams p) {
         }
         // m <- m_hat * alpha' + ((m - alpha * m_hat) / max(sigma, 1e-8)) * sigma'
         const float* lr = p.lut + (size_t)besti * kE + lane * 8;
-        float* st = p.state + tok * kE + lane * 8;
         float nv[8];
 #pragma unroll
         for (int h4 = 0; h4 < 2; ++h4) {
             float4 mh = *reinterpret_cast<const float4*>(lr + h4 * 4);
-            float4 mt = *reinterpret_cast<const float4*>(st + h4 * 4);
+            const float4 mt = mt2[h4];
             float4 o;
             o.x = __fadd_rn(__fmul_rn(mh.x, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.x, -__fmul_rn(p.alpha, mh.x)), sig), p.sigma_next));
             o.y = __fadd_rn(__fmul_rn(mh.y, p.alpha_next), __fmul_rn(__fdiv_rn(__fadd_rn(mt.y, -__fmul_rn(p.alpha, mh.y)), sig), p.sigma_next));
