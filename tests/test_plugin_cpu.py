@@ -228,6 +228,37 @@ def test_shard_bounds_cover_batch():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
+def test_bind_near_gpu_intersects_nvml_mask_and_never_raises(monkeypatch):
+    """bench.py binds each rank to its GPU's NUMA node when N > 1: the helper must take the NVML mask, intersect it with
+    what the process may use, do nothing when that changes nothing, and swallow every failure (no NVML here)."""
+    import sys
+    import types
+    assert D.bind_near_gpu(0) is None                      # this container: no NVML / no GPU
+    have = sorted(os.sched_getaffinity(0))
+    calls = []
+    monkeypatch.setattr(os, "sched_setaffinity", lambda pid, cpus: calls.append((pid, set(cpus))))
+    fake = types.ModuleType("pynvml")
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByUUID = lambda u: (_ for _ in ()).throw(RuntimeError("no uuid"))
+    fake.nvmlDeviceGetHandleByIndex = lambda i: i
+    mask = {"words": None}
+    fake.nvmlDeviceGetCpuAffinity = lambda h, n: mask["words"]
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    words = [0] * ((max(have) // 64) + 1)
+    for c in have:
+        words[c // 64] |= 1 << (c % 64)
+    mask["words"] = list(words)
+    assert D.bind_near_gpu(0) is None and not calls       # the mask is everything we already have: nothing to do
+    if len(have) > 1:
+        words[have[-1] // 64] &= ~(1 << (have[-1] % 64))   # GPU-local set = all but the last CPU
+        mask["words"] = list(words)
+        assert D.bind_near_gpu(0) == have[:-1]
+        assert calls == [(0, set(have[:-1]))]
+    mask["words"] = [0] * len(words)                       # empty intersection: leave the process alone
+    calls.clear()
+    assert D.bind_near_gpu(0) is None and not calls
+
+
 def _gloo_worker(rank, world, port, batch, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
