@@ -246,6 +246,47 @@ class DDP(_DiffusionSegmentorBase):
             seg_logit = resize(seg_logit, size=size, mode="bilinear", align_corners=self.align_corners, warning=False)
         return seg_logit
 
+    def slide_inference(self, img, img_meta, rescale):
+        """encoder_decoder.py:181-227: overlapping crop_size windows at `stride`, each decoded by encode_decode, averaged
+        where they overlap (no shipped DDP config selects it; EncoderDecoder callers may).  Every window has the same size
+        (min(crop, image)) and windows are independent, so `test_cfg.window_batch` of them (default 8) are stacked along the
+        batch axis and decoded by ONE encode_decode call instead of one call per window; the results are added in the
+        reference's (row, column) window order, so equal window logits give bit-equal sums."""
+        cfg = self.test_cfg
+
+        def pair(v):
+            return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+        h_stride, w_stride = pair(cfg["stride"])
+        h_crop, w_crop = pair(cfg["crop_size"])
+        per_call = max(1, int(cfg.get("window_batch", 8)))
+        batch, _, h_img, w_img = img.shape
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        boxes = []
+        for hi in range(h_grids):
+            for wi in range(w_grids):
+                y2 = min(hi * h_stride + h_crop, h_img)
+                x2 = min(wi * w_stride + w_crop, w_img)
+                boxes.append((max(y2 - h_crop, 0), y2, max(x2 - w_crop, 0), x2))
+        preds = img.new_zeros((batch, self.out_channels, h_img, w_img))
+        count = img.new_zeros((batch, 1, h_img, w_img))
+        for i in range(0, len(boxes), per_call):
+            group = boxes[i:i + per_call]
+            crops = torch.cat([img[:, :, y1:y2, x1:x2] for y1, y2, x1, x2 in group], dim=0)
+            logits = self.encode_decode(crops, img_meta)
+            for k, (y1, y2, x1, x2) in enumerate(group):
+                preds[:, :, y1:y2, x1:x2] += logits[k * batch:(k + 1) * batch]
+                count[:, :, y1:y2, x1:x2] += 1
+        assert int((count == 0).sum()) == 0
+        preds = preds / count
+        if rescale:
+            resize_shape = img_meta[0]["img_shape"][:2]
+            preds = preds[:, :, :resize_shape[0], :resize_shape[1]]
+            preds = resize(preds, size=img_meta[0]["ori_shape"][:2], mode="bilinear", align_corners=self.align_corners,
+                           warning=False)
+        return preds
+
     def _fused_view(self, img, img_meta, rescale, accum=None):
         """encode_decode + whole_inference + softmax + flip of `inference` for one view as ONE kernel after the loop
         (ddp_tail_probs): probabilities (b,C,H,W), added into `accum` when given.  None when the view needs the eager path
@@ -265,14 +306,15 @@ class DDP(_DiffusionSegmentorBase):
     def inference(self, img, img_meta, rescale):
         mode = (self.test_cfg or {}).get("mode", "whole")
         assert mode in ["slide", "whole"]
-        if mode == "slide":
-            raise NotImplementedError("slide inference is not used by any DDP config")
         ori_shape = img_meta[0]["ori_shape"] if "ori_shape" in img_meta[0] else None
         assert all(m.get("ori_shape") == ori_shape for m in img_meta)
-        fused = self._fused_view(img, img_meta, rescale)
+        fused = self._fused_view(img, img_meta, rescale)      # None in slide mode
         if fused is not None:
             return fused
-        seg_logit = self.whole_inference(img, img_meta, rescale)
+        if mode == "slide":
+            seg_logit = self.slide_inference(img, img_meta, rescale)
+        else:
+            seg_logit = self.whole_inference(img, img_meta, rescale)
         output = F.softmax(seg_logit, dim=1)
         if img_meta[0].get("flip", False):
             flip_direction = img_meta[0]["flip_direction"]

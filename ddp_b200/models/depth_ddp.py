@@ -79,6 +79,60 @@ class DDP(_DiffusionSegmentorBase):
             raise NotImplementedError("one time embedding per call (the sampling loop uses the same t for every row)")
         return self.engine().head_forward(feat.float(), times[0])
 
+    # ---- callers of the hot path (depth/depth/models/depther/encoder_decoder.py:156-229) ------------
+    def whole_inference(self, img, img_meta, rescale):
+        return self.encode_decode(img, img_meta, rescale)
+
+    @staticmethod
+    def _unflip(pred, meta):
+        """encoder_decoder.py:187-195: a flipped view's prediction is flipped back."""
+        if meta.get("flip", False):
+            direction = meta["flip_direction"]
+            assert direction in ["horizontal", "vertical"]
+            pred = pred.flip(dims=(3,)) if direction == "horizontal" else pred.flip(dims=(2,))
+        return pred
+
+    def _check_view(self, img_meta):
+        mode = (self.test_cfg or {}).get("mode", "whole")
+        assert mode in ["slide", "whole"]
+        ori_shape = img_meta[0]["ori_shape"]
+        assert all(m["ori_shape"] == ori_shape for m in img_meta)
+        if mode == "slide":
+            raise NotImplementedError          # the reference raises here too (encoder_decoder.py:182-183)
+
+    def inference(self, img, img_meta, rescale):
+        """encoder_decoder.py:163-197."""
+        self._check_view(img_meta)
+        return self._unflip(self.whole_inference(img, img_meta, rescale), img_meta[0])
+
     def simple_test(self, img, img_meta, rescale=True):
-        depth_pred = self.encode_decode(img, img_meta, rescale)
+        """encoder_decoder.py:198-208."""
+        return list(self.inference(img, img_meta, rescale).cpu().numpy())
+
+    def aug_test(self, imgs, img_metas, rescale=True):
+        """encoder_decoder.py:210-229: mean of the views' (un-flipped) predictions.  The shipped NYU / KITTI test pipelines
+        are MultiScaleFlipAug with flip=True, i.e. TWO views of the same size per image: consecutive views of equal shape
+        are stacked along the batch axis and decoded by ONE encode_decode call (`test_cfg.batch_views`, default True) —
+        views are independent, and two images per call fill the GPU better than two calls of one.  Summed in view order."""
+        assert rescale
+        n, b = len(imgs), imgs[0].shape[0]
+        batch_views = bool((self.test_cfg or {}).get("batch_views", True))
+        preds, i = [None] * n, 0
+        while i < n:
+            j = i + 1
+            while batch_views and j < n and imgs[j].shape == imgs[i].shape:
+                j += 1
+            if j - i == 1:
+                preds[i] = self.inference(imgs[i], img_metas[i], rescale)
+            else:
+                for k in range(i, j):
+                    self._check_view(img_metas[k])
+                both = self.whole_inference(torch.cat(imgs[i:j], dim=0), img_metas[i], rescale)
+                for k in range(i, j):
+                    preds[k] = self._unflip(both[(k - i) * b:(k - i + 1) * b], img_metas[k][0])
+            i = j
+        depth_pred = preds[0].clone()
+        for k in range(1, n):
+            depth_pred += preds[k]
+        depth_pred /= n
         return list(depth_pred.cpu().numpy())

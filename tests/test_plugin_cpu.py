@@ -74,6 +74,124 @@ def test_depth_plugin_keys():
         assert tuple(got[k].shape) == tuple(want[k].shape), k
 
 
+def _depth_model(test_cfg=None):
+    dh = dict(type="DeformableHeadWithTime", in_channels=[256], channels=256, in_index=[0], dropout_ratio=0.,
+              min_depth=1e-3, max_depth=10, num_feature_levels=1,
+              encoder=dict(type="DetrTransformerEncoder", num_layers=6, transformerlayers=dict(
+                  type="BaseTransformerLayer", use_time_mlp=True,
+                  attn_cfgs=dict(type="MultiScaleDeformableAttention", embed_dims=256, num_levels=1, num_heads=8, dropout=0.),
+                  ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=1024, ffn_drop=0., act_cfg=dict(type="GELU")),
+                  operation_order=("self_attn", "norm", "ffn", "norm"))),
+              positional_encoding=dict(type="SinePositionalEncoding", num_feats=128, normalize=True, offset=-0.5))
+    return build_depther(dict(type="DDP", bit_scale=0.1, timesteps=3, min_depth=1e-3, max_depth=10,
+                              backbone=dict(type="ToyBackbone"), decode_head=dh, test_cfg=test_cfg))
+
+
+def test_depth_aug_test_is_the_mean_of_unflipped_views(monkeypatch):
+    """depth/.../depther/encoder_decoder.py:163-229 with the shipped NYU test pipeline (MultiScaleFlipAug, flip=True: two
+    views per image).  The loop itself needs the GPU; here encode_decode is replaced by a batch-independent function of
+    the pixels, and aug_test (which stacks equal-size views into ONE call) must equal the reference's view-by-view
+    recipe: un-flip every view's prediction, sum in view order, divide."""
+    model = _depth_model(test_cfg=dict(mode="whole"))
+    calls = []
+
+    def fake_encode_decode(img, img_metas, rescale=False):
+        calls.append(tuple(img.shape))
+        ramp = torch.arange(img.shape[3], dtype=torch.float32).view(1, 1, 1, -1) * 0.01
+        return img.mean(1, keepdim=True) * 3.0 + ramp + (0.5 if rescale else 0.0)
+
+    monkeypatch.setattr(model, "encode_decode", fake_encode_decode)
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(2, 3, 12, 20, generator=g)
+    meta = dict(ori_shape=(12, 20, 3), img_shape=(12, 20, 3), flip=False)
+    views = [img, img.flip(3), img.flip(2), torch.randn(2, 3, 6, 10, generator=g)]
+    metas = [[meta] * 2, [dict(meta, flip=True, flip_direction="horizontal")] * 2,
+             [dict(meta, flip=True, flip_direction="vertical")] * 2, [dict(meta, img_shape=(6, 10, 3))] * 2]
+
+    def reference_recipe(vs, ms):
+        total = None
+        for v, m in zip(vs, ms):
+            p = fake_encode_decode(v, m, True)
+            if m[0]["flip"]:
+                p = p.flip(dims=(3,)) if m[0]["flip_direction"] == "horizontal" else p.flip(dims=(2,))
+            total = p if total is None else total + p
+        return total / len(vs)
+
+    want = reference_recipe(views[:3], metas[:3])
+    calls.clear()
+    got = model.forward_test(views[:3], metas[:3])
+    assert calls == [(6, 3, 12, 20)]                                  # three equal-size views: ONE call
+    assert len(got) == 2 and all(torch.equal(torch.from_numpy(a), w) for a, w in zip(got, want))
+    # the same through simple_test for one flipped view
+    one = model.forward_test([views[1]], [metas[1]])
+    assert torch.equal(torch.from_numpy(one[0]), fake_encode_decode(views[1], None, True).flip(3)[0])
+    # batching can be switched off, and views of different sizes are never stacked
+    model.test_cfg = dict(mode="whole", batch_views=False)
+    calls.clear()
+    got2 = model.aug_test(views[:3], metas[:3])
+    assert calls == [(2, 3, 12, 20)] * 3 and all((a == b).all() for a, b in zip(got, got2))
+    model.test_cfg = dict(mode="whole")
+    calls.clear()
+    with pytest.raises(RuntimeError):                                  # the reference's `+=` of a smaller map fails the same way
+        model.aug_test(views[2:], metas[2:])
+    assert calls == [(2, 3, 12, 20), (2, 3, 6, 10)]
+    model.test_cfg = dict(mode="slide")
+    with pytest.raises(NotImplementedError):                           # encoder_decoder.py:182-183
+        model.simple_test(img, [meta] * 2)
+
+
+def test_slide_inference_equals_the_reference_window_loop(monkeypatch):
+    """encoder_decoder.py:181-227 (EncoderDecoder.slide_inference), windows stacked `window_batch` at a time."""
+    import torch.nn.functional as F
+    cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = build_segmentor(cfg.model)
+    C = model.out_channels
+    wgt = torch.randn(C, 3, 1, 1, generator=torch.Generator().manual_seed(5))
+    calls = []
+
+    def fake_encode_decode(img, img_metas):
+        calls.append(tuple(img.shape))
+        yy = torch.arange(img.shape[2], dtype=torch.float32).view(1, 1, -1, 1) * 0.1       # depends on the position IN the window
+        return F.conv2d(img, wgt) + yy
+
+    monkeypatch.setattr(model, "encode_decode", fake_encode_decode)
+
+    def reference_loop(img, h_crop, w_crop, h_stride, w_stride):
+        b, _, h_img, w_img = img.shape
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        preds, count = img.new_zeros((b, C, h_img, w_img)), img.new_zeros((b, 1, h_img, w_img))
+        for hi in range(h_grids):
+            for wi in range(w_grids):
+                y1, x1 = hi * h_stride, wi * w_stride
+                y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
+                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+                lg = fake_encode_decode(img[:, :, y1:y2, x1:x2], None)
+                preds += F.pad(lg, (x1, w_img - x2, y1, h_img - y2))
+                count[:, :, y1:y2, x1:x2] += 1
+        return preds / count
+
+    g = torch.Generator().manual_seed(9)
+    for (h_img, w_img), crop, stride, wb in [((20, 28), (8, 12), (5, 7), 8), ((20, 28), (8, 12), (5, 7), 3),
+                                             ((16, 16), (32, 32), (8, 8), 8), ((17, 23), 8, 6, 1)]:
+        img = torch.randn(2, 3, h_img, w_img, generator=g)
+        model.test_cfg = dict(mode="slide", crop_size=crop, stride=stride, window_batch=wb)
+        cr, st = (crop, crop) if isinstance(crop, int) else crop, (stride, stride) if isinstance(stride, int) else stride
+        want = reference_loop(img, cr[0], cr[1], st[0], st[1])
+        n_windows = len(calls)
+        calls.clear()
+        meta = [dict(ori_shape=(h_img, w_img, 3), img_shape=(h_img, w_img, 3), flip=False)] * 2
+        got = model.slide_inference(img, meta, rescale=False)
+        assert torch.equal(got, want), (h_img, w_img, crop, stride)
+        assert len(calls) == -(-n_windows // wb) and sum(c[0] for c in calls) == 2 * n_windows
+        # through `inference`: softmax of the (rescaled) average
+        out = model.inference(img, meta, rescale=True)
+        assert torch.allclose(out, want.softmax(1), atol=1e-6)
+        calls.clear()
+
+
 def test_constructor_errors_mirror_reference():
     cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
     bad = dict(cfg.model)
