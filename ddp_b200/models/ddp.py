@@ -124,6 +124,10 @@ class _DiffusionSegmentorBase(nn.Module):
     def forward_train(self, *a, **k):
         raise NotImplementedError("training is outside the scope of ddp_b200 (inference hot path only)")
 
+    def forward_dummy(self, img):
+        """encoder_decoder.py:142-146 (tools/get_flops.py, tools/benchmark.py style callers): one encode_decode."""
+        return self.encode_decode(img, None)
+
     def forward(self, img, img_metas, return_loss=False, **kwargs):
         """base.py:96-110."""
         if return_loss:

@@ -138,6 +138,7 @@ def test_depth_aug_test_is_the_mean_of_unflipped_views(monkeypatch):
     model.test_cfg = dict(mode="slide")
     with pytest.raises(NotImplementedError):                           # encoder_decoder.py:182-183
         model.simple_test(img, [meta] * 2)
+    assert torch.equal(model.forward_dummy(img), fake_encode_decode(img, None))      # encoder_decoder.py:122-126
 
 
 def test_slide_inference_equals_the_reference_window_loop(monkeypatch):
