@@ -87,6 +87,29 @@ class _DiffusionSegmentorBase(nn.Module):
     def with_neck(self):
         return hasattr(self, "neck") and self.neck is not None
 
+    @property
+    def with_decode_head(self):
+        return hasattr(self, "decode_head") and self.decode_head is not None
+
+    @property
+    def with_auxiliary_head(self):          # training-only heads are not built (base.py:26-29 reads the attribute)
+        return getattr(self, "auxiliary_head", None) is not None
+
+    @staticmethod
+    def right_pad_dims_to(x, t):
+        """ddp.py:198-202: t with trailing singleton axes up to x's rank."""
+        extra = x.ndim - t.ndim
+        return t if extra <= 0 else t.reshape(*t.shape, *([1] * extra))
+
+    def _sampling_time_pairs(self):
+        from .. import schedule as S
+        return S.sampling_timesteps_seg(self.timesteps, self.time_difference, self.sample_range)
+
+    def _get_sampling_timesteps(self, batch, *, device):
+        """ddp.py:204-213 / depther/ddp.py:210-218: the (t_now, t_next) pairs of the T steps as (2, batch) tensors — the same
+        host function (`ddp_b200.schedule`) the library's per-step constants are computed from."""
+        return [torch.tensor(pair, device=device)[:, None].repeat(1, batch) for pair in self._sampling_time_pairs()]
+
     def extract_feat(self, img):
         x = self.backbone(img)
         if self.with_neck:

@@ -56,6 +56,16 @@ class DDP(_DiffusionSegmentorBase):
                     learned_sinusoidal_dim=self.learned_sinusoidal_dim, num_layers=self.decode_head.encoder.num_layers,
                     min_depth=self.min_depth, max_depth=self.max_depth)
 
+    def _sampling_time_pairs(self):
+        from .. import schedule as S
+        return S.sampling_timesteps_depth(self.timesteps, self.time_difference)
+
+    @staticmethod
+    def gamma(t, ns=0.0002, ds=0.00025):
+        """depther/ddp.py:207-208 (the library receives sqrt(gamma) per step from the same host function)."""
+        from .. import schedule as S
+        return S.gamma(t, ns, ds)
+
     def encode_decode(self, img, img_metas, rescale=False):
         """depth/.../ddp.py:97-110 (the clamp runs inside the library's last step)."""
         x = self.extract_feat(img)[0]

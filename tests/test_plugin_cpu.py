@@ -193,6 +193,30 @@ def test_slide_inference_equals_the_reference_window_loop(monkeypatch):
         calls.clear()
 
 
+def test_sampling_timesteps_and_small_surface_helpers():
+    """ddp.py:198-213, depther/ddp.py:207-218, base.py:21-34: helpers the reference's loop exposes on the model."""
+    cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        seg = build_segmentor(dict(cfg.model, timesteps=4, time_difference=1, sample_range=(0.1, 0.999)))
+    pairs = seg._get_sampling_timesteps(3, device="cpu")
+    assert len(pairs) == 4 and all(tuple(p.shape) == (2, 3) and p.dtype == torch.float32 for p in pairs)
+    for step, p in enumerate(pairs):
+        t_now = 1 - (step / 4) * (1 - 0.1)
+        t_next = max(1 - (step + 1 + 1) / 4 * (1 - 0.1), 0.1)
+        assert torch.equal(p, torch.tensor([[t_now] * 3, [t_next] * 3]))
+    assert float(pairs[-1][1, 0]) == pytest.approx(0.1)                   # clamped at sample_range[0]
+    t = torch.arange(3.0)
+    assert seg.right_pad_dims_to(torch.zeros(3, 4, 5, 6), t).shape == (3, 1, 1, 1) and seg.right_pad_dims_to(t, t) is t
+    assert seg.with_decode_head and not seg.with_auxiliary_head and not seg.with_neck
+    dep = _depth_model()
+    dp = dep._get_sampling_timesteps(2, device="cpu")
+    assert len(dp) == 3 and torch.equal(dp[0], torch.tensor([[1.0, 1.0], [1 - 2 / 3, 1 - 2 / 3]]))
+    assert float(dp[-1][1, 0]) == 0.0
+    tt = torch.tensor([0.0, 0.5, 1.0])
+    assert torch.equal(dep.gamma(tt), torch.cos(((tt + 0.0002) / 1.00025) * torch.pi / 2) ** 2)
+
+
 def test_constructor_errors_mirror_reference():
     cfg = Config.fromfile(os.path.join(HERE, "fixtures", "ddp_toy_config.py"))
     bad = dict(cfg.model)
